@@ -1,0 +1,133 @@
+// Shared declarations for the optimobo_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+
+#include "../../include/optimobo_b200.h"
+
+#define OMBO_NB 64            // Cholesky / triangular-inverse block size
+#define OMBO_PAD 128          // n_pad granularity (GEMM N-chunk)
+#define OMBO_CHUNK (1 << 20)  // candidates scored per pass through the posterior workspace
+
+void ombo_set_error(const char *fmt, ...);
+
+#define OMBO_CUDA(call)                                                              \
+  do {                                                                               \
+    cudaError_t e__ = (call);                                                        \
+    if (e__ != cudaSuccess) {                                                        \
+      ombo_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                   \
+                     cudaGetErrorString(e__));                                       \
+      return OMBO_ERR_CUDA;                                                          \
+    }                                                                                \
+  } while (0)
+
+#define OMBO_CHECK(cond, ...)                                                        \
+  do {                                                                               \
+    if (!(cond)) {                                                                   \
+      ombo_set_error(__VA_ARGS__);                                                   \
+      return OMBO_ERR_INVALID;                                                       \
+    }                                                                                \
+  } while (0)
+
+struct ombo_ctx {
+  int device;
+  int num_sms;
+  int64_t launches;
+  // workspaces (grown on demand, freed in ctx_destroy)
+  void *ws_post;      size_t ws_post_bytes;      // posterior mu/var chunk buffers
+  void *ws_scratch;   size_t ws_scratch_bytes;   // FP64 K* tiles (L2 resident) / fast-path scratch
+  void *ws_partial;   size_t ws_partial_bytes;   // per-block arg-max partials
+  void *ws_stage[2];  size_t ws_stage_bytes;     // host-entry H2D staging (double buffered)
+  void *ws_best;                                  // 16 B device best for the host entry
+  ombo_best *pinned_best;                         // pinned host landing zone
+  cudaStream_t copy_stream;
+  cudaEvent_t ev_copied[2], ev_consumed[2];
+};
+
+int ombo_ws_reserve(void **p, size_t *cur, size_t want);
+
+// ---- state blob layout: a pure function of (n, d) -----------------------------------
+struct GpLayout {
+  int n, d, n_pad;
+  size_t off_L, off_Linv, off_alpha, off_xs, off_status, off_dinv, off_tmp, off_inv_ell;
+  size_t off_bhi, off_blo, off_xs32, off_alpha32;
+  size_t bytes;
+};
+
+static inline int ombo_round_up(int x, int q) { return (x + q - 1) / q * q; }
+
+static inline GpLayout gp_layout(int n, int d) {
+  GpLayout L;
+  L.n = n; L.d = d; L.n_pad = ombo_round_up(n < 1 ? 1 : n, OMBO_PAD);
+  size_t np = (size_t)L.n_pad, off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  L.off_L = take(np * np * 8);
+  L.off_Linv = take(np * np * 8);
+  L.off_alpha = take(np * 8);
+  L.off_xs = take((size_t)d * np * 8);
+  L.off_status = take(16);
+  L.off_dinv = take((np / OMBO_NB) * OMBO_NB * OMBO_NB * 8);
+  L.off_tmp = take(np * 8);
+  L.off_inv_ell = take((size_t)OMBO_MAX_DIM * 8);
+  L.off_bhi = take(np * np * 2);
+  L.off_blo = take(np * np * 2);
+  L.off_xs32 = take(np * 32 * 4);
+  L.off_alpha32 = take(np * 4);
+  L.bytes = off;
+  return L;
+}
+
+// device-side view of one GP used by the scoring kernels
+struct GpDev {
+  int n, n_pad, d, kernel;
+  double sigma_f2, sigma_n2, var_floor;
+  const double *xs;       // (d, n_pad) scaled
+  const double *ell;      // (d) length-scales
+  const double *Linv;     // (n_pad, n_pad)
+  const double *alpha;    // (n_pad)
+  const __nv_bfloat16 *bhi, *blo;
+  const float *xs32, *alpha32;
+};
+
+static inline GpDev gp_dev_view(const ombo_gp &g) {
+  GpLayout L = gp_layout(g.n, g.d);
+  const char *b = (const char *)g.state;
+  GpDev v;
+  v.n = g.n; v.n_pad = L.n_pad; v.d = g.d; v.kernel = g.kernel;
+  v.sigma_f2 = g.sigma_f2; v.sigma_n2 = g.sigma_n2; v.var_floor = g.var_floor;
+  v.xs = (const double *)(b + L.off_xs);
+  v.ell = (const double *)(b + L.off_inv_ell);
+  v.Linv = (const double *)(b + L.off_Linv);
+  v.alpha = (const double *)(b + L.off_alpha);
+  v.bhi = (const __nv_bfloat16 *)(b + L.off_bhi);
+  v.blo = (const __nv_bfloat16 *)(b + L.off_blo);
+  v.xs32 = (const float *)(b + L.off_xs32);
+  v.alpha32 = (const float *)(b + L.off_alpha32);
+  return v;
+}
+
+// candidate pool as the kernels see it
+struct PoolDev {
+  const void *X;      // device rows for this pass (already offset), or nullptr
+  int dtype, d;
+  long long index_base;   // global index of local row 0 of this pass
+  unsigned long long seed;
+  double lo[OMBO_MAX_DIM], span[OMBO_MAX_DIM];
+};
+
+// ---- internal entry points (one per .cu) ------------------------------------------------
+int ombo_refresh_impl(ombo_ctx *ctx, const ombo_gp_spec *spec, void *state, cudaStream_t s);
+int ombo_posterior_fp64(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, long long m,
+                        double *mu, double *var, cudaStream_t s);
+int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, long long m,
+                        double *mu, double *var, cudaStream_t s);
+int ombo_acquire(ombo_ctx *ctx, const ombo_acq *acq, int n_gp, const double *mu, const double *var,
+                 long long m, long long ld, long long index_base, double *out_acq,
+                 ombo_best *best_dev, cudaStream_t s);
+int ombo_best_init(ombo_ctx *ctx, ombo_best *best_dev, cudaStream_t s);
+int ombo_pool_rows_impl(ombo_ctx *ctx, const PoolDev &pool, long long first, long long count,
+                        double *out, cudaStream_t s);

@@ -1,0 +1,328 @@
+// K3 -- GP refresh: K = k(X,X) + (sigma_n2 + jitter) I, L = chol(K), L^-1, alpha = K^-1 y,
+// plus the fast-path operand planes.  Replaces the state GPy builds inside
+// GPRegression(...) after .optimize() (reference call sites: optimisers.py:226-231 etc.;
+// GPy exact_gaussian_inference.py / pdinv / dpotrs).
+//
+// Blocked right-looking FP64 Cholesky with 64x64 blocks: the diagonal block is factorised
+// AND inverted by one CTA in shared memory; the panel solve and the trailing update are
+// 64x64x64 GEMM tiles spread over the whole GPU.  The triangular inverse is column-block
+// parallel (16 columns per CTA, n_pad/16 CTAs), each CTA sweeping down its columns with
+// the pre-inverted diagonal blocks, so no step is a scalar substitution.
+#include "common.cuh"
+
+#define NB OMBO_NB
+#define LDS (NB + 1)
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_prepare(const double *__restrict__ X, const double *__restrict__ y, int n, int d,
+                          int n_pad, const double *__restrict__ ell_dev, double *__restrict__ xs,
+                          float *__restrict__ xs32, double *__restrict__ ypad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  for (int j = 0; j < d; ++j) {
+    double v = (i < n) ? X[(size_t)i * d + j] / ell_dev[j] : 0.0;
+    xs[(size_t)j * n_pad + i] = v;
+  }
+  for (int j = 0; j < 32; ++j) {
+    float v = (i < n && j < d) ? (float)(X[(size_t)i * d + j] / ell_dev[j]) : 0.f;
+    xs32[(size_t)i * 32 + j] = v;
+  }
+  ypad[i] = (i < n) ? y[i] : 0.0;
+}
+
+__device__ __forceinline__ double kernel_of_r2(double r2, double sf2, int kernel) {
+  if (kernel == OMBO_KERNEL_MATERN52) {
+    double r = sqrt(r2);
+    const double s5 = 2.23606797749978969641;
+    return sf2 * (1.0 + s5 * r + (5.0 / 3.0) * r2) * exp(-s5 * r);
+  }
+  return sf2 * exp(-0.5 * r2);
+}
+
+__global__ void k_build_K(const double *__restrict__ xs, int n, int d, int n_pad, double sf2,
+                          double diag_add, int kernel, double *__restrict__ K) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= n_pad || j >= n_pad) return;
+  double v;
+  if (i >= n || j >= n) {
+    v = (i == j) ? 1.0 : 0.0;
+  } else {
+    double r2 = 0.0;
+    for (int t = 0; t < d; ++t) {
+      double df = xs[(size_t)t * n_pad + i] - xs[(size_t)t * n_pad + j];
+      r2 += df * df;
+    }
+    v = kernel_of_r2(r2, sf2, kernel);
+    if (i == j) v += diag_add;
+  }
+  K[(size_t)i * n_pad + j] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// diagonal block: unblocked Cholesky in smem + inverse of the 64x64 triangular factor
+__global__ void __launch_bounds__(256) k_potrf_diag(double *__restrict__ A, int ld, int kb, int n,
+                                                    double *__restrict__ dinv, int *__restrict__ status) {
+  extern __shared__ __align__(16) double dyn_smem[];
+  double (*a)[LDS] = (double (*)[LDS])dyn_smem;
+  double (*inv)[LDS] = (double (*)[LDS])(dyn_smem + NB * LDS);
+  const int tid = threadIdx.x;
+  double *blk = A + ((size_t)kb * NB) * ld + (size_t)kb * NB;
+  for (int e = tid; e < NB * NB; e += 256) a[e / NB][e % NB] = blk[(size_t)(e / NB) * ld + (e % NB)];
+  __syncthreads();
+  for (int j = 0; j < NB; ++j) {
+    if (tid == 0) {
+      double p = a[j][j];
+      if (!(p > 0.0)) {
+        atomicCAS(status, 0, kb * NB + j + 1);
+        p = 1.0;
+      }
+      a[j][j] = sqrt(p);
+    }
+    __syncthreads();
+    if (tid > j && tid < NB) a[tid][j] /= a[j][j];
+    __syncthreads();
+    // trailing update of the lower triangle: a[i][k] -= a[i][j] * a[k][j], j < k <= i
+    for (int e = tid; e < NB * NB; e += 256) {
+      int i = e / NB, k = e % NB;
+      if (k > j && i >= k) a[i][k] -= a[i][j] * a[k][j];
+    }
+    __syncthreads();
+  }
+  // inverse: thread c solves L x = e_c
+  if (tid < NB) {
+    const int c = tid;
+    for (int i = 0; i < NB; ++i) {
+      double s = (i == c) ? 1.0 : 0.0;
+      for (int k = 0; k < i; ++k) s -= a[i][k] * ((k >= c) ? inv[k][c] : 0.0);
+      inv[i][c] = (i >= c) ? s / a[i][i] : 0.0;
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < NB * NB; e += 256) {
+    int i = e / NB, k = e % NB;
+    blk[(size_t)i * ld + k] = (k <= i) ? a[i][k] : 0.0;
+    dinv[(size_t)kb * NB * NB + e] = inv[i][k];
+  }
+}
+
+// C(64x64) (+)= sign * As(64x64) * Bs(64x64)^T with both operands k-contiguous in smem
+__device__ __forceinline__ void gemm64_abt(double (*As)[LDS], double (*Bs)[LDS], double acc[4][4],
+                                           int tr, int tc) {
+#pragma unroll 4
+  for (int t = 0; t < NB; ++t) {
+    double av[4], bv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { av[u] = As[tr + 16 * u][t]; bv[u] = Bs[tc + 16 * u][t]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[u][v] += av[u] * bv[v];
+  }
+}
+
+// L_ik = A_ik * Dinv_k^T   (i > k)
+__global__ void __launch_bounds__(256) k_trsm_panel(double *__restrict__ A, int ld, int kb,
+                                                    const double *__restrict__ dinv) {
+  extern __shared__ __align__(16) double dyn_smem[];
+  double (*As)[LDS] = (double (*)[LDS])dyn_smem;
+  double (*Bs)[LDS] = (double (*)[LDS])(dyn_smem + NB * LDS);
+  const int tid = threadIdx.x;
+  const int ib = kb + 1 + blockIdx.x;
+  double *blk = A + ((size_t)ib * NB) * ld + (size_t)kb * NB;
+  const double *dv = dinv + (size_t)kb * NB * NB;
+  for (int e = tid; e < NB * NB; e += 256) {
+    As[e / NB][e % NB] = blk[(size_t)(e / NB) * ld + (e % NB)];
+    Bs[e / NB][e % NB] = dv[e];
+  }
+  __syncthreads();
+  const int tr = tid / 16, tc = tid % 16;
+  double acc[4][4] = {};
+  gemm64_abt(As, Bs, acc, tr, tc);
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) blk[(size_t)(tr + 16 * u) * ld + (tc + 16 * v)] = acc[u][v];
+}
+
+// A_ij -= L_ik * L_jk^T   (k < j <= i)
+__global__ void __launch_bounds__(256) k_syrk_update(double *__restrict__ A, int ld, int kb) {
+  const int ib = kb + 1 + blockIdx.y;
+  const int jb = kb + 1 + blockIdx.x;
+  if (jb > ib) return;
+  extern __shared__ __align__(16) double dyn_smem[];
+  double (*As)[LDS] = (double (*)[LDS])dyn_smem;
+  double (*Bs)[LDS] = (double (*)[LDS])(dyn_smem + NB * LDS);
+  const int tid = threadIdx.x;
+  const double *Li = A + ((size_t)ib * NB) * ld + (size_t)kb * NB;
+  const double *Lj = A + ((size_t)jb * NB) * ld + (size_t)kb * NB;
+  for (int e = tid; e < NB * NB; e += 256) {
+    As[e / NB][e % NB] = Li[(size_t)(e / NB) * ld + (e % NB)];
+    Bs[e / NB][e % NB] = Lj[(size_t)(e / NB) * ld + (e % NB)];
+  }
+  __syncthreads();
+  const int tr = tid / 16, tc = tid % 16;
+  double acc[4][4] = {};
+  gemm64_abt(As, Bs, acc, tr, tc);
+  double *C = A + ((size_t)ib * NB) * ld + (size_t)jb * NB;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) C[(size_t)(tr + 16 * u) * ld + (tc + 16 * v)] -= acc[u][v];
+}
+
+// ------------------------------------------------------------------------------------------
+// triangular inverse, 16 columns per CTA
+#define TC 16
+__global__ void __launch_bounds__(256) k_trtri_cols(const double *__restrict__ L, int ld, int nb,
+                                                    const double *__restrict__ dinv,
+                                                    double *__restrict__ Linv) {
+  __shared__ double Ls[NB][LDS];       // L tile / Dinv tile
+  __shared__ double Xs[NB][TC + 1];    // X rows of block jb / T
+  const int tid = threadIdx.x;
+  const int c0 = blockIdx.x * TC;
+  const int kb = c0 / NB;
+  const int r = tid % NB;          // output row inside the block row
+  const int cg = (tid / NB) * 4;   // first of 4 output columns
+  for (int ib = kb; ib < nb; ++ib) {
+    double T[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) T[v] = (ib * NB + r == c0 + cg + v) ? 1.0 : 0.0;
+    for (int jb = kb; jb < ib; ++jb) {
+      const double *Lt = L + ((size_t)ib * NB) * ld + (size_t)jb * NB;
+      for (int e = tid; e < NB * NB; e += 256) Ls[e / NB][e % NB] = Lt[(size_t)(e / NB) * ld + (e % NB)];
+      for (int e = tid; e < NB * TC; e += 256)
+        Xs[e / TC][e % TC] = Linv[((size_t)jb * NB + e / TC) * ld + c0 + (e % TC)];
+      __syncthreads();
+#pragma unroll 8
+      for (int t = 0; t < NB; ++t) {
+        double l = Ls[r][t];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) T[v] -= l * Xs[t][cg + v];
+      }
+      __syncthreads();
+    }
+    // X_ib = Dinv_ib * T
+    const double *dv = dinv + (size_t)ib * NB * NB;
+    for (int e = tid; e < NB * NB; e += 256) Ls[e / NB][e % NB] = dv[e];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) Xs[r][cg + v] = T[v];
+    __syncthreads();
+    double o[4] = {0, 0, 0, 0};
+#pragma unroll 8
+    for (int t = 0; t < NB; ++t) {
+      double l = Ls[r][t];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) o[v] += l * Xs[t][cg + v];
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) Linv[((size_t)ib * NB + r) * ld + c0 + cg + v] = o[v];
+    __threadfence_block();
+    __syncthreads();
+  }
+}
+
+// t[j] = sum_i M[j][i] * v[i], i <= j   (one warp per row)
+__global__ void k_trmv_lower(const double *__restrict__ M, int ld, int n_pad, const double *__restrict__ v,
+                             double *__restrict__ out) {
+  int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  int lane = threadIdx.x % 32;
+  if (row >= n_pad) return;
+  double s = 0.0;
+  for (int i = lane; i <= row; i += 32) s += M[(size_t)row * ld + i] * v[i];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[row] = s;
+}
+
+// out[i] = sum_{j >= i} M[j][i] * t[j]    (block (32 cols x 8 row groups))
+__global__ void k_trmv_lower_t(const double *__restrict__ M, int ld, int n_pad, const double *__restrict__ t,
+                               double *__restrict__ out) {
+  __shared__ double part[8][33];
+  int col = blockIdx.x * 32 + threadIdx.x;
+  double s = 0.0;
+  if (col < n_pad)
+    for (int j = col + threadIdx.y; j < n_pad; j += 8) s += M[(size_t)j * ld + col] * t[j];
+  part[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < n_pad) {
+    double a = 0.0;
+    for (int g = 0; g < 8; ++g) a += part[g][threadIdx.x];
+    out[col] = a;
+  }
+}
+
+// zero the padding of L^-1 and emit the fast-path operands:
+//   B = sigma_f2 * L^-1 split into bf16 hi + lo planes, alpha32 = sigma_f2 * alpha
+__global__ void k_finalize(double *__restrict__ Linv, int n, int n_pad, double sf2,
+                           __nv_bfloat16 *__restrict__ bhi, __nv_bfloat16 *__restrict__ blo,
+                           const double *__restrict__ alpha, float *__restrict__ alpha32) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)n_pad * n_pad;
+  if (e >= total) return;
+  int j = (int)(e / n_pad), i = (int)(e % n_pad);
+  double v = Linv[e];
+  if (j >= n || i >= n || i > j) { v = 0.0; Linv[e] = 0.0; }
+  float f = (float)(v * sf2);
+  __nv_bfloat16 h = __float2bfloat16_rn(f);
+  float rem = (float)(v * sf2 - (double)__bfloat162float(h));
+  bhi[e] = h;
+  blo[e] = __float2bfloat16_rn(rem);
+  if (e < (size_t)n_pad) alpha32[e] = (float)(alpha[e] * sf2);
+}
+
+// ------------------------------------------------------------------------------------------
+int ombo_refresh_impl(ombo_ctx *ctx, const ombo_gp_spec *sp, void *state, cudaStream_t s) {
+  const GpLayout lay = gp_layout(sp->n, sp->d);
+  const int n = sp->n, d = sp->d, np = lay.n_pad, nb = np / NB;
+  char *b = (char *)state;
+  double *L = (double *)(b + lay.off_L), *Linv = (double *)(b + lay.off_Linv);
+  double *alpha = (double *)(b + lay.off_alpha), *xs = (double *)(b + lay.off_xs);
+  int *status = (int *)(b + lay.off_status);
+  double *dinv = (double *)(b + lay.off_dinv), *tmp = (double *)(b + lay.off_tmp);
+  double *ell_dev = (double *)(b + lay.off_inv_ell);
+  __nv_bfloat16 *bhi = (__nv_bfloat16 *)(b + lay.off_bhi), *blo = (__nv_bfloat16 *)(b + lay.off_blo);
+  float *xs32 = (float *)(b + lay.off_xs32), *alpha32 = (float *)(b + lay.off_alpha32);
+
+  OMBO_CUDA(cudaMemcpyAsync(ell_dev, sp->ell, sizeof(double) * d, cudaMemcpyHostToDevice, s));
+  OMBO_CUDA(cudaMemsetAsync(status, 0, 16, s));
+  OMBO_CUDA(cudaMemsetAsync(Linv, 0, (size_t)np * np * 8, s));
+  k_prepare<<<(np + 127) / 128, 128, 0, s>>>(sp->X, sp->y, n, d, np, ell_dev, xs, xs32, alpha /*ypad*/);
+  dim3 tb(16, 16), gb(np / 16, np / 16);
+  k_build_K<<<gb, tb, 0, s>>>(xs, n, d, np, sp->sigma_f2, sp->sigma_n2 + sp->jitter, sp->kernel, L);
+  ctx->launches += 2;
+  const size_t sm2 = (size_t)2 * NB * LDS * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    OMBO_CUDA(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+    OMBO_CUDA(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+    OMBO_CUDA(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+    attr_set = true;
+  }
+  for (int kb = 0; kb < nb; ++kb) {
+    k_potrf_diag<<<1, 256, sm2, s>>>(L, np, kb, n, dinv, status);
+    ctx->launches += 1;
+    int rem = nb - kb - 1;
+    if (rem > 0) {
+      k_trsm_panel<<<rem, 256, sm2, s>>>(L, np, kb, dinv);
+      k_syrk_update<<<dim3(rem, rem), 256, sm2, s>>>(L, np, kb);
+      ctx->launches += 2;
+    }
+  }
+  k_trtri_cols<<<np / TC, 256, 0, s>>>(L, np, nb, dinv, Linv);
+  // alpha = Linv^T (Linv y); ypad currently lives in alpha
+  k_trmv_lower<<<(np + 7) / 8, 256, 0, s>>>(Linv, np, np, alpha, tmp);
+  k_trmv_lower_t<<<(np + 31) / 32, dim3(32, 8), 0, s>>>(Linv, np, np, tmp, alpha);
+  size_t total = (size_t)np * np;
+  k_finalize<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Linv, n, np, sp->sigma_f2, bhi, blo, alpha, alpha32);
+  ctx->launches += 4;
+  OMBO_CUDA(cudaGetLastError());
+  int hstatus[4] = {0, 0, 0, 0};
+  OMBO_CUDA(cudaMemcpyAsync(hstatus, status, 16, cudaMemcpyDeviceToHost, s));
+  OMBO_CUDA(cudaStreamSynchronize(s));
+  if (hstatus[0] != 0) {
+    ombo_set_error("gp_refresh: matrix not positive definite at row %d (raise jitter and retry)", hstatus[0] - 1);
+    return OMBO_ERR_NOT_PD;
+  }
+  return OMBO_OK;
+}

@@ -1,0 +1,137 @@
+"""GP surrogate whose posterior is evaluated by the CUDA hot path.
+
+`GPModel` stands where the reference puts a `GPy.models.GPRegression(X, y, Matern52(ARD))`
+(optimobo/algorithms/optimisers.py:226-231 and the other sites listed in SURVEY.md section 0.1)
+and answers BOTH model surfaces the reference calls:
+
+  * GPy:     predict(Xnew (m,d))            -> (mean (m,1), var (m,1))   variance clipped at 1e-15
+  * sklearn: predict(X, return_std=True)    -> (mean (m,),  std (m,))    negative variance -> 0
+             (util_functions.py:265)
+
+so the reference's own `util_functions.EHVI` etc. run unmodified on it.  PyTorch tensors hold
+the training set and the state blob (L, L^-1, alpha, fast-path planes); all arithmetic happens
+in liboptimobo_b200.so.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import types
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+_KERNELS = {"matern52": _cabi.KERNEL_MATERN52, "rbf": _cabi.KERNEL_RBF}
+
+
+def _as_device(device):
+    dev = torch.device(device if device is not None else "cuda:0")
+    if dev.type != "cuda":
+        raise RuntimeError("optimobo_b200 runs on CUDA devices only (no CPU fallback)")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def current_stream_ptr(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class GPModel:
+    """Exact GP regression state (zero-mean, no y-normalisation, like GPRegression's defaults)."""
+
+    def __init__(self, X, y, lengthscale, variance=1.0, noise=0.0, jitter=1e-8, kernel="matern52",
+                 device=None, refresh=True, max_jitter_tries=6):
+        self.device = _as_device(device)
+        self.X = torch.as_tensor(np.asarray(X, dtype=np.float64) if not torch.is_tensor(X) else X,
+                                 dtype=torch.float64).to(self.device).contiguous()
+        if self.X.dim() != 2:
+            raise ValueError("X must be (n, d)")
+        self.y = torch.as_tensor(np.asarray(y, dtype=np.float64) if not torch.is_tensor(y) else y,
+                                 dtype=torch.float64).to(self.device).reshape(-1).contiguous()
+        self.n, self.d = self.X.shape
+        if self.y.numel() != self.n:
+            raise ValueError("y must have one value per row of X")
+        if kernel not in _KERNELS:
+            raise ValueError(f"unknown kernel {kernel!r} (matern52 | rbf)")
+        self.kernel_name = kernel
+        self.kernel = _KERNELS[kernel]
+        self.lengthscale = np.broadcast_to(np.asarray(lengthscale, dtype=np.float64), (self.d,)).copy()
+        self.variance = float(variance)
+        self.noise = float(noise)
+        self.jitter = float(jitter)
+        self.max_jitter_tries = max_jitter_tries
+        self.n_pad = _cabi.lib().ombo_n_pad(self.n)
+        self.state = torch.empty(_cabi.state_bytes(self.n, self.d), dtype=torch.uint8, device=self.device)
+        # read by TuRBO in the reference (turbo.py:83); kept for surface compatibility
+        self.kern = types.SimpleNamespace(lengthscale=self.lengthscale, variance=self.variance)
+        self.refreshed = False
+        if refresh:
+            self.refresh()
+
+    # ---- K3 ------------------------------------------------------------------------------
+    def refresh(self):
+        """(Re)builds L, L^-1, alpha on the device.  On a non-PD matrix the jitter is raised
+        x10 per try starting from mean(diag K) * 1e-6, like GPy's jitchol."""
+        ctx = _cabi.Context.get(self.device.index)
+        ell = (C.c_double * self.d)(*self.lengthscale.tolist())
+        jitter = self.jitter
+        for attempt in range(self.max_jitter_tries + 1):
+            spec = _cabi.GpSpec(n=self.n, d=self.d, kernel=self.kernel, reserved=0,
+                                sigma_f2=self.variance, sigma_n2=self.noise, jitter=jitter,
+                                X=self.X.data_ptr(), y=self.y.data_ptr(), ell=ell)
+            with torch.cuda.device(self.device):
+                rc = _cabi.lib().ombo_gp_refresh(ctx.handle, C.byref(spec), C.c_void_p(self.state.data_ptr()),
+                                                 current_stream_ptr(self.device))
+            if rc == _cabi.ERR_NOT_PD and attempt < self.max_jitter_tries:
+                base = (self.variance + self.noise) * 1e-6
+                jitter = base if jitter < base else jitter * 10.0
+                continue
+            _cabi.check(rc)
+            break
+        self.effective_jitter = jitter
+        self.refreshed = True
+        return self
+
+    def _field(self, field, dtype, shape):
+        off, cnt = _cabi.state_field(self.n, self.d, field)
+        esz = torch.empty((), dtype=dtype).element_size()
+        return self.state[off:off + cnt * esz].view(dtype).view(*shape)
+
+    @property
+    def L(self):
+        return self._field(_cabi.FIELD_L, torch.float64, (self.n_pad, self.n_pad))[: self.n, : self.n]
+
+    @property
+    def Linv(self):
+        return self._field(_cabi.FIELD_LINV, torch.float64, (self.n_pad, self.n_pad))[: self.n, : self.n]
+
+    @property
+    def alpha(self):
+        return self._field(_cabi.FIELD_ALPHA, torch.float64, (self.n_pad,))[: self.n]
+
+    def c_struct(self, var_floor=1e-15):
+        if not self.refreshed:
+            raise RuntimeError("GPModel.refresh() has not been run")
+        return _cabi.Gp(n=self.n, d=self.d, kernel=self.kernel, reserved=0, sigma_f2=self.variance,
+                        sigma_n2=self.noise, var_floor=var_floor, state=self.state.data_ptr())
+
+    # ---- the two model surfaces ------------------------------------------------------------
+    def predict(self, Xnew, return_std=False, precision="fp64"):
+        from .acquisition import posterior
+        Xn = np.atleast_2d(np.asarray(Xnew.detach().cpu() if torch.is_tensor(Xnew) else Xnew, dtype=np.float64))
+        mu, var = posterior([self], Xn, precision=precision, var_floor=0.0 if return_std else 1e-15)
+        mu = mu[0].cpu().numpy()
+        var = var[0].cpu().numpy()
+        if return_std:
+            return mu, np.sqrt(np.maximum(var, 0.0))
+        return mu.reshape(-1, 1), var.reshape(-1, 1)
+
+    @classmethod
+    def from_gpy(cls, gpy_model, device=None):
+        """Adopts the hyper-parameters of a fitted GPy GPRegression (reference models)."""
+        kern = gpy_model.kern
+        return cls(np.asarray(gpy_model.X), np.asarray(gpy_model.Y).reshape(-1),
+                   np.asarray(kern.lengthscale), float(kern.variance),
+                   noise=float(gpy_model.Gaussian_noise.variance), device=device)
