@@ -100,6 +100,7 @@ enum { OMBO_FIELD_L = 0,      /* (n_pad, n_pad) f64 lower Cholesky factor       
 };
 
 int ombo_abi_version(void);
+int ombo_has_fast_path(void);   /* 1 when OMBO_PREC_FAST (tcgen05) is compiled in */
 const char *ombo_last_error(void);
 
 int ombo_ctx_create(int device, ombo_ctx **out);
@@ -177,6 +178,17 @@ int ombo_acquire_posterior(ombo_ctx *ctx, const ombo_acq *acq, int n_gp, const d
 /* regenerates rows [index, index+count) of a counter-generated pool into DEVICE out (count,d) f64 */
 int ombo_pool_rows(ombo_ctx *ctx, const ombo_pool *pool, int64_t index, int64_t count,
                    double *out, void *stream);
+
+/* C1 support: packs the 16-byte best into ONE order-preserving signed 64-bit key for a single
+ * NCCL all-reduce(MAX): high 32 bits = order-preserving image of (float)value, low 32 bits =
+ * 0xFFFFFFFF - global index (so ties resolve to the lowest index, like np.argmax).  key_dev is
+ * DEVICE int64; it can be the NCCL send buffer itself.  Requires 0 <= index < 2^32. */
+int ombo_pack_key(ombo_ctx *ctx, const ombo_best *best_dev, int64_t *key_dev, void *stream);
+
+/* Per-kernel timing of the dominant (posterior) kernel with CUDA events recorded on the
+ * launching stream: enable, run, synchronise, then read the launch count and total duration. */
+int ombo_profile_enable(ombo_ctx *ctx, int enable);
+int ombo_profile_read(ombo_ctx *ctx, int64_t *n_launches, double *total_ms);
 
 /* number of kernels this library launched since the counter was last reset (bench.py's
  * gpu_launches) */

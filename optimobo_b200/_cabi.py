@@ -23,9 +23,10 @@ SEM_REFERENCE, SEM_EXACT = 0, 1
  FIELD_ALPHA32) = range(9)
 
 EXPORTS = [
-    "ombo_abi_version", "ombo_last_error", "ombo_ctx_create", "ombo_ctx_destroy", "ombo_n_pad",
+    "ombo_abi_version", "ombo_has_fast_path", "ombo_last_error", "ombo_ctx_create", "ombo_ctx_destroy", "ombo_n_pad",
     "ombo_gp_state_bytes", "ombo_gp_state_field", "ombo_gp_refresh", "ombo_score",
     "ombo_score_host", "ombo_acquire_posterior", "ombo_pool_rows", "ombo_launch_count",
+    "ombo_pack_key", "ombo_profile_enable", "ombo_profile_read",
 ]
 
 
@@ -101,12 +102,19 @@ def lib():
     L.ombo_acquire_posterior.argtypes = [C.c_void_p, C.POINTER(Acq), C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                          C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ombo_pool_rows.argtypes = [C.c_void_p, C.POINTER(Pool), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+    L.ombo_pack_key.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ombo_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.ombo_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.ombo_launch_count.argtypes = [C.c_void_p, C.c_int]
     L.ombo_launch_count.restype = C.c_int64
     for name in EXPORTS:
         getattr(L, name)
     _lib = L
     return L
+
+
+def fast_path_available() -> bool:
+    return bool(lib().ombo_has_fast_path())
 
 
 def check(rc):
@@ -150,6 +158,14 @@ class Context:
 
     def launch_count(self, reset=False) -> int:
         return int(lib().ombo_launch_count(self.handle, 1 if reset else 0))
+
+    def profile(self, enable=True):
+        check(lib().ombo_profile_enable(self.handle, 1 if enable else 0))
+
+    def profile_read(self):
+        n, ms = C.c_int64(), C.c_double()
+        check(lib().ombo_profile_read(self.handle, C.byref(n), C.byref(ms)))
+        return int(n.value), float(ms.value)
 
     def close(self):
         if self.handle:

@@ -287,6 +287,23 @@ __global__ void __launch_bounds__(1024) k_argmax_final(const ombo_best *__restri
 
 __global__ void k_best_init(ombo_best *best) { best->value = -INFINITY; best->index = -1; }
 
+__global__ void k_pack_key(const ombo_best *__restrict__ best, long long *__restrict__ key) {
+  float f = (float)best->value;
+  unsigned bits = __float_as_uint(f);
+  unsigned ord = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+  long long idx = best->index;
+  unsigned low = (idx < 0 || idx > 0xFFFFFFFFll) ? 0u : (0xFFFFFFFFu - (unsigned)idx);
+  long long hi = (long long)ord - 2147483648ll;            // signed, order-preserving
+  *key = (hi << 32) | (long long)low;
+}
+
+int ombo_pack_key_impl(ombo_ctx *ctx, const ombo_best *best_dev, long long *key_dev, cudaStream_t s) {
+  k_pack_key<<<1, 1, 0, s>>>(best_dev, key_dev);
+  ctx->launches += 1;
+  OMBO_CUDA(cudaGetLastError());
+  return OMBO_OK;
+}
+
 int ombo_best_init(ombo_ctx *ctx, ombo_best *best_dev, cudaStream_t s) {
   k_best_init<<<1, 1, 0, s>>>(best_dev);
   ctx->launches += 1;

@@ -28,6 +28,7 @@ int ombo_ws_reserve(void **p, size_t *cur, size_t want) {
 extern "C" {
 
 int ombo_abi_version(void) { return OMBO_ABI_VERSION; }
+int ombo_has_fast_path(void) { return ombo_fast_path_built(); }
 const char *ombo_last_error(void) { return g_err; }
 
 int ombo_ctx_create(int device, ombo_ctx **out) {
@@ -75,6 +76,7 @@ int ombo_ctx_destroy(ombo_ctx *c) {
     cudaEventDestroy(c->ev_copied[i]);
     cudaEventDestroy(c->ev_consumed[i]);
   }
+  if (c->prof_ev[0]) for (int i = 0; i < 2 * OMBO_PROF_MAX; ++i) cudaEventDestroy(c->prof_ev[i]);
   if (c->ws_best) cudaFree(c->ws_best);
   if (c->pinned_best) cudaFreeHost(c->pinned_best);
   cudaStreamDestroy(c->copy_stream);
@@ -310,6 +312,38 @@ int ombo_pool_rows(ombo_ctx *ctx, const ombo_pool *pool, int64_t index, int64_t 
   k_pool_rows<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pd, index - pool->index_base, count, out);
   ctx->launches += 1;
   OMBO_CUDA(cudaGetLastError());
+  return OMBO_OK;
+}
+
+int ombo_pack_key(ombo_ctx *ctx, const ombo_best *best_dev, int64_t *key_dev, void *stream) {
+  OMBO_CHECK(ctx && best_dev && key_dev, "pack_key: NULL argument");
+  OMBO_CUDA(cudaSetDevice(ctx->device));
+  return ombo_pack_key_impl(ctx, best_dev, (long long *)key_dev, (cudaStream_t)stream);
+}
+
+int ombo_profile_enable(ombo_ctx *ctx, int enable) {
+  OMBO_CHECK(ctx != nullptr, "profile_enable: NULL ctx");
+  OMBO_CUDA(cudaSetDevice(ctx->device));
+  if (enable && !ctx->prof_ev[0])
+    for (int i = 0; i < 2 * OMBO_PROF_MAX; ++i) OMBO_CUDA(cudaEventCreate(&ctx->prof_ev[i]));
+  ctx->prof_enabled = enable ? 1 : 0;
+  ctx->prof_count = 0;
+  return OMBO_OK;
+}
+
+int ombo_profile_read(ombo_ctx *ctx, int64_t *n_launches, double *total_ms) {
+  OMBO_CHECK(ctx && n_launches && total_ms, "profile_read: NULL argument");
+  OMBO_CUDA(cudaSetDevice(ctx->device));
+  double tot = 0.0;
+  for (int i = 0; i < ctx->prof_count; ++i) {
+    OMBO_CUDA(cudaEventSynchronize(ctx->prof_ev[2 * i + 1]));
+    float ms = 0.f;
+    OMBO_CUDA(cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]));
+    tot += ms;
+  }
+  *n_launches = ctx->prof_count;
+  *total_ms = tot;
+  ctx->prof_count = 0;
   return OMBO_OK;
 }
 

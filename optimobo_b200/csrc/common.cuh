@@ -11,6 +11,7 @@
 
 #define OMBO_NB 64            // Cholesky / triangular-inverse block size
 #define OMBO_PAD 128          // n_pad granularity (GEMM N-chunk)
+#define OMBO_PROF_MAX 4096
 #define OMBO_CHUNK (1 << 20)  // candidates scored per pass through the posterior workspace
 
 void ombo_set_error(const char *fmt, ...);
@@ -46,6 +47,22 @@ struct ombo_ctx {
   ombo_best *pinned_best;                         // pinned host landing zone
   cudaStream_t copy_stream;
   cudaEvent_t ev_copied[2], ev_consumed[2];
+  // optional per-launch timing of the posterior kernels
+  int prof_enabled;
+  int prof_count;
+  cudaEvent_t prof_ev[2 * OMBO_PROF_MAX];
+};
+
+// brackets one posterior-kernel launch with events when profiling is on
+struct ProfScope {
+  ombo_ctx *c; cudaStream_t s; int slot;
+  ProfScope(ombo_ctx *ctx, cudaStream_t st) : c(ctx), s(st), slot(-1) {
+    if (c->prof_enabled && c->prof_count < OMBO_PROF_MAX) {
+      slot = c->prof_count++;
+      cudaEventRecord(c->prof_ev[2 * slot], s);
+    }
+  }
+  ~ProfScope() { if (slot >= 0) cudaEventRecord(c->prof_ev[2 * slot + 1], s); }
 };
 
 int ombo_ws_reserve(void **p, size_t *cur, size_t want);
@@ -125,9 +142,11 @@ int ombo_posterior_fp64(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
                         double *mu, double *var, cudaStream_t s);
 int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, long long m,
                         double *mu, double *var, cudaStream_t s);
+int ombo_fast_path_built();
 int ombo_acquire(ombo_ctx *ctx, const ombo_acq *acq, int n_gp, const double *mu, const double *var,
                  long long m, long long ld, long long index_base, double *out_acq,
                  ombo_best *best_dev, cudaStream_t s);
 int ombo_best_init(ombo_ctx *ctx, ombo_best *best_dev, cudaStream_t s);
+int ombo_pack_key_impl(ombo_ctx *ctx, const ombo_best *best_dev, long long *key_dev, cudaStream_t s);
 int ombo_pool_rows_impl(ombo_ctx *ctx, const PoolDev &pool, long long first, long long count,
                         double *out, cudaStream_t s);

@@ -60,7 +60,7 @@ k_posterior_fp64(GpDev gp, PoolDev pool, long long m, double *__restrict__ scrat
   double *xc = (double *)smem_raw;                 // phase A: [TM][d]
   double *xt = xc + TM * d;                        // phase A: [d][TCH]
   __shared__ double red_mu[TM];
-  __shared__ double red_ss[TM];
+  __shared__ double red_ss[4][TM];   // one slot per N-warp: fixed-order sum, bit-reproducible
 
   const long long num_tiles = (m + TM - 1) / TM;
   for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -72,7 +72,7 @@ k_posterior_fp64(GpDev gp, PoolDev pool, long long m, double *__restrict__ scrat
       long long cg = c0 + c;
       xc[e] = (cg < m) ? ombo_pool_coord(pool, cg, j) / gp.ell[j] : 0.0;
     }
-    if (tid < TM) { red_mu[tid] = 0.0; red_ss[tid] = 0.0; }
+    if (tid < TM) red_mu[tid] = 0.0;
     for (int i0 = 0; i0 < np; i0 += TCH) {
       __syncthreads();
       for (int e = tid; e < d * TCH; e += 256) {
@@ -165,13 +165,13 @@ k_posterior_fp64(GpDev gp, PoolDev pool, long long m, double *__restrict__ scrat
       double s = ss[u];
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (t4 == 0) atomicAdd(&red_ss[32 * wm + 8 * u + g8], s);
+      if (t4 == 0) red_ss[wn][32 * wm + 8 * u + g8] = s;
     }
     __syncthreads();
     if (tid < TM) {
       long long cg = c0 + tid;
       if (cg < m) {
-        double v = gp.sigma_f2 - red_ss[tid];
+        double v = gp.sigma_f2 - (((red_ss[0][tid] + red_ss[1][tid]) + red_ss[2][tid]) + red_ss[3][tid]);
         v = fmax(v, gp.var_floor) + gp.sigma_n2;
         mu_out[cg] = red_mu[tid];
         var_out[cg] = v;
@@ -196,7 +196,10 @@ int ombo_posterior_fp64(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
   size_t want = (size_t)grid * TM * gp.n_pad * 8;
   int rc = ombo_ws_reserve(&ctx->ws_scratch, &ctx->ws_scratch_bytes, want);
   if (rc) return rc;
-  k_posterior_fp64<<<grid, 256, smem, s>>>(gp, pool, m, (double *)ctx->ws_scratch, mu, var);
+  {
+    ProfScope prof(ctx, s);
+    k_posterior_fp64<<<grid, 256, smem, s>>>(gp, pool, m, (double *)ctx->ws_scratch, mu, var);
+  }
   ctx->launches += 1;
   OMBO_CUDA(cudaGetLastError());
   return OMBO_OK;

@@ -101,7 +101,9 @@ class GPModel:
 
     @property
     def L(self):
-        return self._field(_cabi.FIELD_L, torch.float64, (self.n_pad, self.n_pad))[: self.n, : self.n]
+        # only the lower triangle of the working matrix is the factor (the strict upper blocks
+        # still hold K)
+        return torch.tril(self._field(_cabi.FIELD_L, torch.float64, (self.n_pad, self.n_pad))[: self.n, : self.n])
 
     @property
     def Linv(self):
