@@ -25,7 +25,7 @@ __global__ void k_prepare(const double *__restrict__ X, const double *__restrict
   }
   for (int j = 0; j < 32; ++j) {
     float v = (i < n && j < d) ? (float)(X[(size_t)i * d + j] / ell_dev[j]) : 0.f;
-    xs32[(size_t)i * 32 + j] = v;
+    xs32[(size_t)j * n_pad + i] = v;
   }
   ypad[i] = (i < n) ? y[i] : 0.0;
 }

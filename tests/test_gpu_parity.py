@@ -371,3 +371,55 @@ def test_errors_are_loud():
         pass
     with pytest.raises(TypeError):
         ob.spec_expected_decomposition([.5, .5], Custom([0, 0], [1, 1]), 0.1, np.zeros((8, 2)))
+
+
+# ------------------------------------------------------------------------------------------
+# fast mode: bf16x3 split on tcgen05 (rtol 1e-3, north_star; atol 1e-3 of the output scale
+# because sigma -> 0 / mu -> 0 make a pure relative bound meaningless)
+# ------------------------------------------------------------------------------------------
+FAST_CASES = [(128, 10, 1000), (256, 10, 1 << 14), (512, 12, 1 << 13), (1024, 10, 1 << 13), (700, 7, 5001),
+              (100, 4, 129), (1536, 10, 2048)]
+
+
+@pytest.mark.parametrize("n,d,m", FAST_CASES)
+def test_posterior_fast_vs_oracle(n, d, m):
+    if not _cabi.fast_path_available():
+        pytest.skip("fast path not built")
+    X, Y, ells, sf2 = make_problem(n, d)
+    Xc = np.random.default_rng(9).random((m, d))
+    for i in range(2):
+        gp = ob.GPModel(X, Y[:, i], ells[i], sf2[i], device=DEV)
+        st = O.gp_fit_state(X, Y[:, i], ells[i], sf2[i])
+        mu_o, var_o = O.gp_posterior(st, Xc)
+        mu, var = ob.posterior([gp], Xc, precision="fast")
+        mu, var = mu[0].cpu().numpy(), var[0].cpu().numpy()
+        np.testing.assert_allclose(mu, mu_o, rtol=1e-3, atol=1e-3 * np.abs(mu_o).max())
+        np.testing.assert_allclose(np.sqrt(var), np.sqrt(var_o), rtol=1e-3, atol=1e-3 * np.sqrt(sf2[i]))
+        # and against the FP64 CUDA path: same tolerance
+        mu64, var64 = ob.posterior([gp], Xc, precision="fp64")
+        np.testing.assert_allclose(np.sqrt(var), np.sqrt(var64[0].cpu().numpy()), rtol=1e-3, atol=1e-3 * np.sqrt(sf2[i]))
+        # bit-reproducible run to run
+        mu_b, var_b = ob.posterior([gp], Xc, precision="fast")
+        assert torch.equal(mu_b[0].cpu(), torch.as_tensor(mu)) and torch.equal(var_b[0].cpu(), torch.as_tensor(var))
+
+
+def test_full_path_fast_ehvi_selection():
+    if not _cabi.fast_path_available():
+        pytest.skip("fast path not built")
+    n, d, m = 1024, 10, 1 << 15
+    X, Y, ells, sf2 = make_problem(n, d)
+    models = [ob.GPModel(X, Y[:, i], ells[i], sf2[i], device=DEV) for i in range(2)]
+    lo, hi = np.zeros(d), np.ones(d)
+    pool = ob.CandidatePool.counter(m, lo, hi, seed=1)
+    cache = ob.host_prep.cached_samples(2, 5, seed=0)
+    PF, r = ob.host_prep.calc_pf(Y), Y.max(0)
+    spec = ob.spec_ehvi(r, PF, cache, "exact")
+    fast = ob.score(models, spec, pool, precision="fast", want_acq=True)
+    ref = ob.score(models, spec, pool, precision="fp64", want_acq=True)
+    a_f, a_r = fast.acq.cpu().numpy(), ref.acq.cpu().numpy()
+    np.testing.assert_allclose(a_f, a_r, rtol=5e-3, atol=2e-3 * np.abs(a_r).max())
+    # identical selection whenever the top-two gap exceeds the tolerance
+    order = np.argsort(-a_r)
+    if a_r[order[0]] - a_r[order[1]] > 5e-3 * a_r[order[0]]:
+        assert fast.best_index == ref.best_index
+    assert a_r[fast.best_index] >= a_r[order[0]] * (1 - 5e-3)
