@@ -11,7 +11,7 @@
 //   warp 1      MMA issuer (one elected lane): 12 tcgen05.mma (4 k-steps x 3 products) per (chunk, K-block)
 //   warp 2      TMEM allocator (512 columns = 4 accumulator slots of 128 columns)
 //   warps 4-7   epilogue: tcgen05.ld 32x32b (one candidate row per thread), square + row-sum
-//   warps 8-23  K1 generators: scaled distances by direct differences in FP32, Matern-5/2 / RBF via
+//   warps 8-15  K1 generators: scaled distances by direct differences in FP32, Matern-5/2 / RBF via
 //               MUFU (sqrt, ex2), bf16 hi/lo split, written straight into the UMMA K-major
 //               SWIZZLE_128B operand layout in shared memory (3-stage ring), and the mean.
 // L^-1 is lower triangular: column chunk c (128 rows of L^-1) only needs K-blocks kb <= 2c+1, the rest
@@ -20,15 +20,20 @@
 // Within a pass the loop is K-outer, so a chunk's accumulator completes as soon as the K loop crosses
 // its diagonal and the epilogue drains it while the tensor core continues on the later chunks.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "candidates.cuh"
 
 #define FM 128            // candidates per tile (UMMA M)
 #define FN 128            // columns per accumulator chunk (UMMA N)
 #define FK 64             // K-block: 64 bf16 = 128 B = one swizzle atom row
+#ifndef NSTA
 #define NSTA 3            // A ring stages (hi+lo = 32 KB each)
+#endif
+#ifndef NSTB
 #define NSTB 3            // B ring stages (hi+lo = 32 KB each)
-#define GEN_WARPS 16
+#endif
+#define GEN_WARPS 8        // one generator warp per 8-column (16-byte) operand chunk of the K-block
 #define GEN_THREADS (GEN_WARPS * 32)
 #define FAST_THREADS ((8 + GEN_WARPS) * 32)
 #define PLANE_BYTES (FM * 128)          // 16 KB
@@ -62,6 +67,23 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try(bar, parity)) {}
 }
+// polling warps steal issue slots from the K1 generators: back off between probes
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try(bar, parity)) __nanosleep(ns);
+}
+// one lane of a CONVERGED warp; unlike `lane == 0` the compiler knows a single thread is active, so
+// tcgen05 / TMA operands stay in uniform registers without a per-instruction waterfall loop
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
@@ -73,6 +95,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n"
@@ -114,10 +155,14 @@ struct FastParams {
   PoolDev pool;
   long long m;
   double *mu_out, *var_out;
+  int dbg;   // bit 0: skip the MMAs, bit 1: skip the K1 math (timing experiments only; results are garbage)
 };
 
 extern __shared__ __align__(1024) unsigned char fast_smem[];
 
+// DP = input dimension padded to the instantiated size (padding coordinates are zero on both sides),
+// R = candidate rows held in registers per generator thread (4 when DP <= 12, else 2)
+template <int DP, int R>
 __global__ void __launch_bounds__(FAST_THREADS, 1)
 k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                  const FastParams prm) {
@@ -126,21 +171,25 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
   const int n_chunks = np / FN;
   const int n_pass = (n_chunks + 3) / 4;
   const long long n_tiles = (prm.m + FM - 1) / FM;
+  // every CTA of a cluster must walk the same (tile, chunk, K-block) sequence: the B tiles are multicast
+  const long long n_iter = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const uint32_t cs = cluster_size(), crank = cluster_rank();
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
 
   // ---- shared memory carve-up ----
   unsigned char *sA = fast_smem + ((1024u - (smem_u32(fast_smem) & 1023u)) & 1023u);   // SWIZZLE_128B: 1024-B aligned
   unsigned char *sB = sA + NSTA * STAGE_BYTES;                 // NSTB x (hi 16 KB, lo 16 KB)
-  float *xc = (float *)(sB + NSTB * STAGE_BYTES);              // [d][128] scaled candidate coords
-  float *xt = xc + (size_t)d * FM;                             // [2][(d+1)][64] train slice (+ alpha row)
-  float *mu_sm = xt + 2 * (size_t)(d + 1) * FK;                // [4][128]
-  uint64_t *bars = (uint64_t *)(((uintptr_t)(mu_sm + 4 * FM) + 15) & ~(uintptr_t)15);
+  float *xc = (float *)(sB + NSTB * STAGE_BYTES);              // [DP][128] scaled candidate coords
+  float *xt = xc + (size_t)DP * FM;                            // [2][(DP+1)][64] train slice (+ alpha row)
+  float *mu_sm = xt + 2 * (size_t)(DP + 1) * FK;               // [GEN_WARPS][128]
+  uint64_t *bars = (uint64_t *)(((uintptr_t)(mu_sm + GEN_WARPS * FM) + 15) & ~(uintptr_t)15);
   uint64_t *a_full = bars, *a_empty = bars + NSTA, *b_full = bars + 2 * NSTA, *b_empty = b_full + NSTB;
   uint64_t *t_full = b_empty + NSTB, *t_empty = t_full + 4;
   uint32_t *tmem_slot = (uint32_t *)(t_empty + 4);
 
   if (tid == 0) {
     for (int s = 0; s < NSTA; ++s) { mbar_init(smem_u32(&a_full[s]), GEN_WARPS); mbar_init(smem_u32(&a_empty[s]), 1); }
-    for (int s = 0; s < NSTB; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
+    for (int s = 0; s < NSTB; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), cs); }
     for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&t_full[s]), 1); mbar_init(smem_u32(&t_empty[s]), 4); }
     fence_mbar_init();
   }
@@ -150,25 +199,34 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();          // remote CTAs arrive on / multicast into this CTA's barriers
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // =============================== TMA producer (B tiles) ===============================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t st = 0, ph = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (long long it = 0; it < n_iter; ++it) {
+      const long long tile = blockIdx.x + it * gridDim.x;
         for (int p = 0; p < n_pass; ++p) {
           const int c_first = 4 * p, c_last = min(4 * p + 3, n_chunks - 1);
           const int kb_end = 2 * c_last + 2;
           for (int kb = 0; kb < kb_end; ++kb) {
             for (int c = max(c_first, kb >> 1); c <= c_last; ++c) {
-              mbar_wait(smem_u32(&b_empty[st]), ph ^ 1);
+              mbar_wait_sleep(smem_u32(&b_empty[st]), ph ^ 1, 64);
               const uint32_t full = smem_u32(&b_full[st]);
               mbar_expect_tx(full, STAGE_BYTES);
               const uint32_t dst = smem_u32(sB + st * STAGE_BYTES);
-              tma_load_2d(dst, &map_hi, full, kb * FK, c * FN);
-              tma_load_2d(dst + PLANE_BYTES, &map_lo, full, kb * FK, c * FN);
+              if (cs == 1) {
+                tma_load_2d(dst, &map_hi, full, kb * FK, c * FN);
+                tma_load_2d(dst + PLANE_BYTES, &map_lo, full, kb * FK, c * FN);
+              } else {                       // this CTA fetches rows [crank, crank+1) * FN/cs and multicasts them
+                const int rows = FN / (int)cs;
+                const uint32_t sl = (uint32_t)(crank * rows * 128);
+                tma_load_2d_mc(dst + sl, &map_hi, full, kb * FK, c * FN + (int)crank * rows, cmask);
+                tma_load_2d_mc(dst + PLANE_BYTES + sl, &map_lo, full, kb * FK, c * FN + (int)crank * rows, cmask);
+              }
               if (++st == NSTB) { st = 0; ph ^= 1; }
             }
           }
@@ -177,27 +235,29 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===========================================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, tph = 0;   // tph: per-slot phase bits of t_empty
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (long long it = 0; it < n_iter; ++it) {
+      const long long tile = blockIdx.x + it * gridDim.x;
         for (int p = 0; p < n_pass; ++p) {
           const int c_first = 4 * p, c_last = min(4 * p + 3, n_chunks - 1);
           const int kb_end = 2 * c_last + 2;
           for (int kb = 0; kb < kb_end; ++kb) {
-            mbar_wait(smem_u32(&a_full[sa]), pa);
+            mbar_wait_sleep(smem_u32(&a_full[sa]), pa, 32);
             tc_fence_after();
             const uint32_t a_hi = smem_u32(sA + sa * STAGE_BYTES), a_lo = a_hi + PLANE_BYTES;
             for (int c = max(c_first, kb >> 1); c <= c_last; ++c) {
               const int slot = c & 3;
               if (kb == 0) {                                  // first touch of this accumulator slot
-                mbar_wait(smem_u32(&t_empty[slot]), ((tph >> slot) & 1) ^ 1);
+                mbar_wait_sleep(smem_u32(&t_empty[slot]), ((tph >> slot) & 1) ^ 1, 32);
                 tph ^= (1u << slot);
                 tc_fence_after();
               }
-              mbar_wait(smem_u32(&b_full[sb]), pb);
+              mbar_wait_sleep(smem_u32(&b_full[sb]), pb, 32);
               tc_fence_after();
               const uint32_t b_hi = smem_u32(sB + sb * STAGE_BYTES), b_lo = b_hi + PLANE_BYTES;
               const uint32_t dcol = tmem_base + (uint32_t)(slot * FN);
+              if (!(prm.dbg & 1))
 #pragma unroll
               for (int ks = 0; ks < FK / 16; ++ks) {
                 const uint64_t dah = make_sdesc(a_hi + ks * 32), dal = make_sdesc(a_lo + ks * 32);
@@ -206,7 +266,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                 umma_bf16(dcol, dal, dbh, FAST_IDESC, 1u);
                 umma_bf16(dcol, dah, dbl, FAST_IDESC, 1u);
               }
-              umma_commit(smem_u32(&b_empty[sb]));
+              if (cs == 1) umma_commit(smem_u32(&b_empty[sb])); else umma_commit_mc(smem_u32(&b_empty[sb]), cmask);
               if (kb == 2 * c + 1) umma_commit(smem_u32(&t_full[slot]));     // chunk complete
               if (++sb == NSTB) { sb = 0; pb ^= 1; }
             }
@@ -221,11 +281,12 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     const int quad = warp - 4;
     const int row = quad * 32 + lane;
     uint32_t fph = 0;                                        // per-slot phase bits of t_full
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (long long it = 0; it < n_iter; ++it) {
+      const long long tile = blockIdx.x + it * gridDim.x;
       double ss = 0.0;
       for (int c = 0; c < n_chunks; ++c) {
         const int slot = c & 3;
-        mbar_wait(smem_u32(&t_full[slot]), (fph >> slot) & 1);
+        mbar_wait_sleep(smem_u32(&t_full[slot]), (fph >> slot) & 1, 200);
         fph ^= (1u << slot);
         tc_fence_after();
         float part[4] = {0.f, 0.f, 0.f, 0.f};
@@ -250,134 +311,175 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     }
   } else if (warp >= 8) {
     // =============================== K1 generators ========================================
-    const int gt = tid - 8 * 32;                 // 0..511
-    const int row = gt & (FM - 1);
-    const int qp = gt >> 7;                      // 0..3: K columns [16 qp, 16 qp + 16) of the block
-    const int gwarp = warp - 8;
+    // Warp q owns operand chunk q (K columns 8q..8q+7 of the block); lane l owns candidate rows
+    // l + 32 rr.  The candidate coordinates live in registers for the whole tile, so the only
+    // shared-memory reads in the inner loop are two broadcast LDS.128 of (negated) training
+    // coordinates per dimension: the LSU traffic that competes with the UMMA operand fetch is
+    // 1/R of a row-per-thread mapping.
+    const int gt = tid - 8 * 32;                 // 0..255
+    const int q = gt >> 5;                       // chunk / warp index 0..7
     const bool matern = (prm.gp.kernel == OMBO_KERNEL_MATERN52);
-    const uint32_t swz_row = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
-    const uint32_t off0 = swz_row + (uint32_t)((((2 * qp) ^ (row & 7)) & 7) << 4);
-    const uint32_t off1 = swz_row + (uint32_t)((((2 * qp + 1) ^ (row & 7)) & 7) << 4);
+    constexpr int RB = 4 / R;                    // row batches per K-block
+    constexpr int XT_STRIDE = (DP + 1) * FK;
     uint32_t sa = 0, pa = 0;
     int xbuf = 0;
-    const int xt_stride = (d + 1) * FK;
-    // train-slice loader role of this thread: row jj of the slice (jj < d: coords, jj == d: alpha), 4 floats
+    // train-slice loader: 16 float4 per row, 16 rows per sweep; rows < DP are NEGATED coords, row DP = alpha
     const int ld_j = gt >> 4, ld_o = (gt & 15) * 4;
-    auto load_slice = [&](int kb) -> float4 {
+    constexpr int LD_SWEEPS = (DP + 1 + 15) / 16;
+    auto load_row = [&](int jj, int kb) -> float4 {
       float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ld_j < d) r = *(const float4 *)(prm.gp.xs32 + (size_t)ld_j * np + kb * FK + ld_o);
-      else if (ld_j == d) r = *(const float4 *)(prm.gp.alpha32 + kb * FK + ld_o);
+      if (jj < d) {
+        r = *(const float4 *)(prm.gp.xs32 + (size_t)jj * np + kb * FK + ld_o);
+        r.x = -r.x; r.y = -r.y; r.z = -r.z; r.w = -r.w;
+      } else if (jj == DP) {
+        r = *(const float4 *)(prm.gp.alpha32 + kb * FK + ld_o);
+      }
       return r;
     };
-    // first slice
-    {
-      float4 r = load_slice(0);
-      if (ld_j <= d) *(float4 *)(xt + ld_j * FK + ld_o) = r;
+#pragma unroll
+    for (int sw = 0; sw < LD_SWEEPS; ++sw) {
+      const int jj = ld_j + 16 * sw;
+      if (jj <= DP) *(float4 *)(xt + jj * FK + ld_o) = load_row(jj, 0);
     }
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (long long it = 0; it < n_iter; ++it) {
+      const long long tile = blockIdx.x + it * gridDim.x;
       asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
-      for (int e = gt; e < FM * d; e += GEN_THREADS) {
+      for (int e = gt; e < FM * DP; e += GEN_THREADS) {
         const int r_ = e & (FM - 1), j = e >> 7;
         const long long cg = tile * FM + r_;
-        xc[j * FM + r_] = (cg < prm.m) ? (float)(ombo_pool_coord(prm.pool, cg, j) / prm.gp.ell[j]) : 0.f;
+        xc[j * FM + r_] = (cg < prm.m && j < d) ? (float)(ombo_pool_coord(prm.pool, cg, j) / prm.gp.ell[j]) : 0.f;
       }
       asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
-      float mu_acc = 0.f;
+      float mu_acc[4] = {0.f, 0.f, 0.f, 0.f};
       for (int p = 0; p < n_pass; ++p) {
         const int c_last = min(4 * p + 3, n_chunks - 1);
         const int kb_end = 2 * c_last + 2;
         const bool do_mu = (p == n_pass - 1);
         for (int kb = 0; kb < kb_end; ++kb) {
           const int kb_next = (kb + 1 < kb_end) ? kb + 1 : 0;
-          const float4 nxt = load_slice(kb_next);            // prefetch the next train slice
-          const float *xs = xt + xbuf * xt_stride;
-          float r2[16];
+          float4 nxt[LD_SWEEPS];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) r2[e] = 0.f;
-          for (int j = 0; j < d; ++j) {
-            const float x = xc[j * FM + row];
-            const float4 *tp = (const float4 *)(xs + j * FK + 16 * qp);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 t = tp[q];
-              float d0 = x - t.x, d1 = x - t.y, d2 = x - t.z, d3 = x - t.w;
-              r2[4 * q + 0] = fmaf(d0, d0, r2[4 * q + 0]);
-              r2[4 * q + 1] = fmaf(d1, d1, r2[4 * q + 1]);
-              r2[4 * q + 2] = fmaf(d2, d2, r2[4 * q + 2]);
-              r2[4 * q + 3] = fmaf(d3, d3, r2[4 * q + 3]);
-            }
-          }
-          float kv[16];
-          if (matern) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              float r;
-              asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(r2[e]));
-              float ex;
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(r * -3.2259955597f));   // -sqrt(5) * log2(e)
-              kv[e] = fmaf(r, 2.2360679775f, fmaf(r2[e], 1.6666666667f, 1.0f)) * ex;
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              float ex;
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(r2[e] * -0.7213475204f));  // -0.5 * log2(e)
-              kv[e] = ex;
-            }
-          }
-          if (do_mu) {
-            const float4 *ap = (const float4 *)(xs + d * FK + 16 * qp);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 a = ap[q];
-              mu_acc = fmaf(kv[4 * q + 0], a.x, mu_acc);
-              mu_acc = fmaf(kv[4 * q + 1], a.y, mu_acc);
-              mu_acc = fmaf(kv[4 * q + 2], a.z, mu_acc);
-              mu_acc = fmaf(kv[4 * q + 3], a.w, mu_acc);
-            }
-          }
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(kv[2 * e], kv[2 * e + 1]);
-            uint32_t hb = *reinterpret_cast<uint32_t *>(&h);
-            float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xffff0000u);
-            __nv_bfloat162 l = __floats2bfloat162_rn(kv[2 * e] - h0, kv[2 * e + 1] - h1);
-            hi[e] = hb;
-            lo[e] = *reinterpret_cast<uint32_t *>(&l);
-          }
-          // wait for the MMA to have released this A stage, then publish
-          mbar_wait(smem_u32(&a_empty[sa]), pa ^ 1);
+          for (int sw = 0; sw < LD_SWEEPS; ++sw) nxt[sw] = load_row(ld_j + 16 * sw, kb_next);   // prefetch
+          const float *xs = xt + xbuf * XT_STRIDE + 8 * q;
           unsigned char *st_hi = sA + sa * STAGE_BYTES, *st_lo = st_hi + PLANE_BYTES;
-          *(uint4 *)(st_hi + off0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *(uint4 *)(st_hi + off1) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-          *(uint4 *)(st_lo + off0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          *(uint4 *)(st_lo + off1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          if (prm.dbg & 2) mbar_wait_sleep(smem_u32(&a_empty[sa]), pa ^ 1, 32);
+#pragma unroll 1
+          for (int rb = 0; rb < ((prm.dbg & 2) ? 0 : RB); ++rb) {
+            float x[R][DP];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+              for (int j = 0; j < DP; ++j) x[rr][j] = xc[j * FM + lane + 32 * (R * rb + rr)];
+            float2 r2[R][4];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) r2[rr][e] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < DP; ++j) {
+              const float4 t0 = *(const float4 *)(xs + j * FK);
+              const float4 t1 = *(const float4 *)(xs + j * FK + 4);
+#pragma unroll
+              for (int rr = 0; rr < R; ++rr) {
+                const float2 xx = make_float2(x[rr][j], x[rr][j]);
+                const float2 d0 = __fadd2_rn(xx, make_float2(t0.x, t0.y));
+                const float2 d1 = __fadd2_rn(xx, make_float2(t0.z, t0.w));
+                const float2 d2 = __fadd2_rn(xx, make_float2(t1.x, t1.y));
+                const float2 d3 = __fadd2_rn(xx, make_float2(t1.z, t1.w));
+                r2[rr][0] = __ffma2_rn(d0, d0, r2[rr][0]);
+                r2[rr][1] = __ffma2_rn(d1, d1, r2[rr][1]);
+                r2[rr][2] = __ffma2_rn(d2, d2, r2[rr][2]);
+                r2[rr][3] = __ffma2_rn(d3, d3, r2[rr][3]);
+              }
+            }
+            const float4 al0 = *(const float4 *)(xs + DP * FK);
+            const float4 al1 = *(const float4 *)(xs + DP * FK + 4);
+            if (rb == 0) mbar_wait_sleep(smem_u32(&a_empty[sa]), pa ^ 1, 32);   // stage released by the MMA
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+              float2 kv[4];
+              if (matern) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 rad, ex;
+                  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad.x) : "f"(r2[rr][e].x));
+                  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad.y) : "f"(r2[rr][e].y));
+                  const float2 arg = __fmul2_rn(rad, make_float2(-3.2259955597f, -3.2259955597f));   // -sqrt5 log2(e)
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.x) : "f"(arg.x));
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.y) : "f"(arg.y));
+                  const float2 poly = __ffma2_rn(rad, make_float2(2.2360679775f, 2.2360679775f),
+                                                 __ffma2_rn(r2[rr][e], make_float2(1.6666666667f, 1.6666666667f),
+                                                            make_float2(1.0f, 1.0f)));
+                  kv[e] = __fmul2_rn(poly, ex);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 arg = __fmul2_rn(r2[rr][e], make_float2(-0.7213475204f, -0.7213475204f));  // -0.5 log2(e)
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(kv[e].x) : "f"(arg.x));
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(kv[e].y) : "f"(arg.y));
+                }
+              }
+              if (do_mu) {
+                float2 m2 = __fmul2_rn(kv[0], make_float2(al0.x, al0.y));
+                m2 = __ffma2_rn(kv[1], make_float2(al0.z, al0.w), m2);
+                m2 = __ffma2_rn(kv[2], make_float2(al1.x, al1.y), m2);
+                m2 = __ffma2_rn(kv[3], make_float2(al1.z, al1.w), m2);
+                mu_acc[R * rb + rr] += m2.x + m2.y;
+              }
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 h = __float22bfloat162_rn(kv[e]);
+                const uint32_t hb = *reinterpret_cast<uint32_t *>(&h);
+                // k' > 0, so setting the sign bit negates the bf16 hi part
+                const float2 nh = make_float2(__uint_as_float((hb << 16) | 0x80000000u),
+                                              __uint_as_float((hb & 0xffff0000u) | 0x80000000u));
+                __nv_bfloat162 l = __float22bfloat162_rn(__fadd2_rn(kv[e], nh));
+                hi[e] = hb;
+                lo[e] = *reinterpret_cast<uint32_t *>(&l);
+              }
+              const int row = lane + 32 * (R * rb + rr);
+              const uint32_t off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((q ^ (row & 7)) & 7) << 4));
+              *(uint4 *)(st_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *(uint4 *)(st_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&a_full[sa]));
           if (++sa == NSTA) { sa = 0; pa ^= 1; }
           // install the prefetched slice in the other buffer
-          if (ld_j <= d) *(float4 *)(xt + (xbuf ^ 1) * xt_stride + ld_j * FK + ld_o) = nxt;
+          float *xn = xt + (xbuf ^ 1) * XT_STRIDE;
+#pragma unroll
+          for (int sw = 0; sw < LD_SWEEPS; ++sw) {
+            const int jj = ld_j + 16 * sw;
+            if (jj <= DP) *(float4 *)(xn + jj * FK + ld_o) = nxt[sw];
+          }
           asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
           xbuf ^= 1;
         }
       }
-      // mean: 4 partial sums per candidate row
-      mu_sm[qp * FM + row] = mu_acc;
+      // mean: one partial sum per (chunk warp, row)
+#pragma unroll
+      for (int r4 = 0; r4 < 4; ++r4) mu_sm[q * FM + lane + 32 * r4] = mu_acc[r4];
       asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
-      if (qp == 0) {
-        const long long cg = tile * FM + row;
-        if (cg < prm.m)
-          prm.mu_out[cg] = (double)((mu_sm[row] + mu_sm[FM + row]) + (mu_sm[2 * FM + row] + mu_sm[3 * FM + row]));
+      if (gt < FM) {
+        const long long cg = tile * FM + gt;
+        if (cg < prm.m) {
+          float acc = 0.f;
+#pragma unroll
+          for (int w = 0; w < GEN_WARPS; ++w) acc += mu_sm[w * FM + gt];
+          prm.mu_out[cg] = (double)acc;
+        }
       }
     }
-    (void)gwarp;
   }
 
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();          // nobody exits while a peer may still signal / multicast to it
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u));
   }
@@ -400,12 +502,12 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int make_b_map(CUtensorMap *map, const void *base, int n_pad) {
+static int make_b_map(CUtensorMap *map, const void *base, int n_pad, int cs) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { ombo_set_error("cuTensorMapEncodeTiled is not available from the driver"); return OMBO_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)n_pad, (cuuint64_t)n_pad};
   cuuint64_t strides[1] = {(cuuint64_t)n_pad * 2};
-  cuuint32_t box[2] = {FK, FN};
+  cuuint32_t box[2] = {FK, (cuuint32_t)(FN / cs)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -416,29 +518,63 @@ static int make_b_map(CUtensorMap *map, const void *base, int n_pad) {
 
 int ombo_fast_path_built() { return 1; }
 
+template <int DP, int R>
+static int launch_fast(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensorMap &map_lo, const FastParams &prm,
+                       int grid, int cs, cudaStream_t s) {
+  const size_t smem = (size_t)(NSTA + NSTB) * STAGE_BYTES + (size_t)DP * FM * 4 + 2 * (size_t)(DP + 1) * FK * 4 +
+                      GEN_WARPS * FM * 4 + 16 + (2 * NSTA + 2 * NSTB + 8) * 8 + 16 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast<DP, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  ProfScope prof(ctx, s);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(FAST_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  OMBO_CUDA(cudaLaunchKernelEx(&cfg, k_posterior_fast<DP, R>, map_hi, map_lo, prm));
+  return OMBO_OK;
+}
+
 int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, long long m, double *mu, double *var,
                         cudaStream_t s) {
   if (m <= 0) return OMBO_OK;
-  CUtensorMap map_hi, map_lo;
-  int rc = make_b_map(&map_hi, gp.bhi, gp.n_pad);
-  if (rc) return rc;
-  rc = make_b_map(&map_lo, gp.blo, gp.n_pad);
-  if (rc) return rc;
-  const size_t smem = (size_t)(NSTA + NSTB) * STAGE_BYTES + (size_t)gp.d * FM * 4 + 2 * (size_t)(gp.d + 1) * FK * 4 +
-                      4 * FM * 4 + 16 + (2 * NSTA + 2 * NSTB + 8) * 8 + 16 + 1024;
-  static size_t attr = 0;
-  if (smem > attr) {
-    OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+  if (gp.d > 24) {
+    ombo_set_error("fast precision mode supports d <= 24 (got %d); use OMBO_PREC_FP64", gp.d);
+    return OMBO_ERR_UNSUPPORTED;
   }
+  int cs = 2;                                  // CTAs per cluster sharing each multicast B tile
+  { const char *e = getenv("OMBO_FAST_CLUSTER"); if (e) cs = atoi(e); }
+  if (cs != 1 && cs != 2 && cs != 4) cs = 2;
+  long long tiles = (m + FM - 1) / FM;
+  if (tiles < cs) cs = 1;
+  CUtensorMap map_hi, map_lo;
+  int rc = make_b_map(&map_hi, gp.bhi, gp.n_pad, cs);
+  if (rc) return rc;
+  rc = make_b_map(&map_lo, gp.blo, gp.n_pad, cs);
+  if (rc) return rc;
   FastParams prm;
   prm.gp = gp; prm.pool = pool; prm.m = m; prm.mu_out = mu; prm.var_out = var;
-  long long tiles = (m + FM - 1) / FM;
+  { const char *e = getenv("OMBO_FAST_DBG"); prm.dbg = e ? atoi(e) : 0; }
   int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
-  {
-    ProfScope prof(ctx, s);
-    k_posterior_fast<<<grid, FAST_THREADS, smem, s>>>(map_hi, map_lo, prm);
-  }
+  grid = grid / cs * cs;                       // whole clusters; the uniform iteration count covers the remainder
+  const int d = gp.d;
+  if (d <= 2) rc = launch_fast<2, 4>(ctx, map_hi, map_lo, prm, grid, cs, s);
+  else if (d <= 4) rc = launch_fast<4, 4>(ctx, map_hi, map_lo, prm, grid, cs, s);
+  else if (d <= 6) rc = launch_fast<6, 4>(ctx, map_hi, map_lo, prm, grid, cs, s);
+  else if (d <= 8) rc = launch_fast<8, 4>(ctx, map_hi, map_lo, prm, grid, cs, s);
+  else if (d <= 10) rc = launch_fast<10, 4>(ctx, map_hi, map_lo, prm, grid, cs, s);
+  else if (d <= 12) rc = launch_fast<12, 4>(ctx, map_hi, map_lo, prm, grid, cs, s);
+  else if (d <= 16) rc = launch_fast<16, 2>(ctx, map_hi, map_lo, prm, grid, cs, s);
+  else rc = launch_fast<24, 2>(ctx, map_hi, map_lo, prm, grid, cs, s);
+  if (rc) return rc;
   ctx->launches += 1;
   OMBO_CUDA(cudaGetLastError());
   return OMBO_OK;
