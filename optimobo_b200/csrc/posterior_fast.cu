@@ -84,6 +84,12 @@ __device__ __forceinline__ uint32_t elect_one() {
       : "=r"(pred));
   return pred;
 }
+__device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, unsigned ns, long long &acc, bool on) {
+  if (!on) { mbar_wait_sleep(bar, parity, ns); return; }
+  long long t0 = clock64();
+  mbar_wait_sleep(bar, parity, ns);
+  acc += clock64() - t0;
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
@@ -114,6 +120,40 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+// arrive / expect_tx on a barrier that may live in the peer CTA of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 2-SM TMA load: data lands in this CTA's smem, the transaction bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+      "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {     // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n"
@@ -148,35 +188,48 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
   return ((uint64_t)hi << 32) | lo;
 }
 // instruction descriptor: D = f32, A = B = bf16, both K-major, N = 128, M = 128
-#define FAST_IDESC ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FN >> 3) << 17) | ((uint32_t)(FM >> 4) << 24))
 
 struct FastParams {
   GpDev gp;
   PoolDev pool;
   long long m;
   double *mu_out, *var_out;
+  long long *prof;   // optional per-CTA wait-cycle counters (timing experiments)
   int dbg;   // bit 0: skip the MMAs, bit 1: skip the K1 math (timing experiments only; results are garbage)
 };
 
 extern __shared__ __align__(1024) unsigned char fast_smem[];
 
-// DP = input dimension padded to the instantiated size (padding coordinates are zero on both sides),
-// R = candidate rows held in registers per generator thread (4 when DP <= 12, else 2)
-template <int DP, int R>
+// DP   = input dimension padded to the instantiated size (padding coordinates are zero on both sides)
+// R    = candidate rows held in registers per generator thread (4 when DP <= 12, else 2)
+// PAIR = cta_group::2: two CTAs of a cluster form one UMMA M = 256 x N = 256 tile pair.  Each CTA generates
+//        the K* rows of its own 128 candidates and TMA-loads only ITS half of the B tile; the leader CTA
+//        issues the MMAs for both tensor cores.  Per MAC this halves the shared-memory operand traffic,
+//        which is what bounds the single-CTA variant (8 KB of operands per 128x128x16 MMA = the full
+//        128 B/clk of the SM's shared memory, before the TMA and K1 writes are even counted).
+template <int DP, int R, bool PAIR>
 __global__ void __launch_bounds__(FAST_THREADS, 1)
 k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                  const FastParams prm) {
+  constexpr int CW = PAIR ? 256 : 128;           // accumulator chunk width = UMMA N
+  constexpr int NSLOT = 512 / CW;                // TMEM accumulator slots
+  constexpr int KSH = PAIR ? 2 : 1;              // chunk c needs K-blocks kb < (c + 1) << KSH
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CW >> 3) << 17) |
+                             ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = prm.gp.d, np = prm.gp.n_pad;
-  const int n_chunks = np / FN;
-  const int n_pass = (n_chunks + 3) / 4;
+  const int nkb = np / FK;
+  const int n_chunks = (np + CW - 1) / CW;
+  const int n_pass = (n_chunks + NSLOT - 1) / NSLOT;
   const long long n_tiles = (prm.m + FM - 1) / FM;
-  // every CTA of a cluster must walk the same (tile, chunk, K-block) sequence: the B tiles are multicast
+  // every CTA of a cluster walks the same (tile, chunk, K-block) sequence
   const long long n_iter = (n_tiles + gridDim.x - 1) / gridDim.x;
   const uint32_t cs = cluster_size(), crank = cluster_rank();
   const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+  const bool leader = !PAIR || crank == 0;
+  auto last_kb = [&](int c) { return min(((c + 1) << KSH) - 1, nkb - 1); };
 
-  // ---- shared memory carve-up ----
+  // ---- shared memory carve-up (identical in every CTA: the pair's UMMA descriptors rely on it) ----
   unsigned char *sA = fast_smem + ((1024u - (smem_u32(fast_smem) & 1023u)) & 1023u);   // SWIZZLE_128B: 1024-B aligned
   unsigned char *sB = sA + NSTA * STAGE_BYTES;                 // NSTB x (hi 16 KB, lo 16 KB)
   float *xc = (float *)(sB + NSTB * STAGE_BYTES);              // [DP][128] scaled candidate coords
@@ -188,18 +241,29 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
   uint32_t *tmem_slot = (uint32_t *)(t_empty + 4);
 
   if (tid == 0) {
-    for (int s = 0; s < NSTA; ++s) { mbar_init(smem_u32(&a_full[s]), GEN_WARPS); mbar_init(smem_u32(&a_empty[s]), 1); }
-    for (int s = 0; s < NSTB; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), cs); }
-    for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&t_full[s]), 1); mbar_init(smem_u32(&t_empty[s]), 4); }
+    for (int s = 0; s < NSTA; ++s) {
+      mbar_init(smem_u32(&a_full[s]), PAIR ? 2 * GEN_WARPS : GEN_WARPS);
+      mbar_init(smem_u32(&a_empty[s]), 1);
+    }
+    for (int s = 0; s < NSTB; ++s) {
+      mbar_init(smem_u32(&b_full[s]), PAIR ? 2 : 1);
+      mbar_init(smem_u32(&b_empty[s]), PAIR ? 1 : cs);
+    }
+    for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&t_full[s]), 1); mbar_init(smem_u32(&t_empty[s]), PAIR ? 8 : 4); }
     fence_mbar_init();
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (cs > 1) cluster_sync_all();          // remote CTAs arrive on / multicast into this CTA's barriers
+  if (cs > 1) cluster_sync_all();          // peers arrive on / write into this CTA's barriers and smem
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -207,74 +271,95 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     // =============================== TMA producer (B tiles) ===============================
     if (elect_one()) {
       uint32_t st = 0, ph = 0;
+      long long w_bempty = 0; const bool pon = prm.prof != nullptr; const long long t_start = clock64();
       for (long long it = 0; it < n_iter; ++it) {
-      const long long tile = blockIdx.x + it * gridDim.x;
         for (int p = 0; p < n_pass; ++p) {
-          const int c_first = 4 * p, c_last = min(4 * p + 3, n_chunks - 1);
-          const int kb_end = 2 * c_last + 2;
+          const int c_first = NSLOT * p, c_last = min(c_first + NSLOT - 1, n_chunks - 1);
+          const int kb_end = last_kb(c_last) + 1;
           for (int kb = 0; kb < kb_end; ++kb) {
-            for (int c = max(c_first, kb >> 1); c <= c_last; ++c) {
-              mbar_wait_sleep(smem_u32(&b_empty[st]), ph ^ 1, 64);
-              const uint32_t full = smem_u32(&b_full[st]);
-              mbar_expect_tx(full, STAGE_BYTES);
+            for (int c = max(c_first, kb >> KSH); c <= c_last; ++c) {
+              mbar_wait_prof(smem_u32(&b_empty[st]), ph ^ 1, 64, w_bempty, pon);
               const uint32_t dst = smem_u32(sB + st * STAGE_BYTES);
-              if (cs == 1) {
-                tma_load_2d(dst, &map_hi, full, kb * FK, c * FN);
-                tma_load_2d(dst + PLANE_BYTES, &map_lo, full, kb * FK, c * FN);
-              } else {                       // this CTA fetches rows [crank, crank+1) * FN/cs and multicasts them
-                const int rows = FN / (int)cs;
-                const uint32_t sl = (uint32_t)(crank * rows * 128);
-                tma_load_2d_mc(dst + sl, &map_hi, full, kb * FK, c * FN + (int)crank * rows, cmask);
-                tma_load_2d_mc(dst + PLANE_BYTES + sl, &map_lo, full, kb * FK, c * FN + (int)crank * rows, cmask);
+              if (PAIR) {                    // this CTA's half of the 256-row B tile; bytes counted on the leader
+                const uint32_t full = mapa_rank(smem_u32(&b_full[st]), 0);
+                mbar_expect_tx_cluster(full, STAGE_BYTES);
+                tma_load_2d_2sm(dst, &map_hi, full, kb * FK, c * CW + (int)crank * 128);
+                tma_load_2d_2sm(dst + PLANE_BYTES, &map_lo, full, kb * FK, c * CW + (int)crank * 128);
+              } else {
+                const uint32_t full = smem_u32(&b_full[st]);
+                mbar_expect_tx(full, STAGE_BYTES);
+                if (cs == 1) {
+                  tma_load_2d(dst, &map_hi, full, kb * FK, c * CW);
+                  tma_load_2d(dst + PLANE_BYTES, &map_lo, full, kb * FK, c * CW);
+                } else {                     // this CTA fetches rows [crank, crank+1) * 128/cs and multicasts them
+                  const int rows = 128 / (int)cs;
+                  const uint32_t sl = (uint32_t)(crank * rows * 128);
+                  tma_load_2d_mc(dst + sl, &map_hi, full, kb * FK, c * CW + (int)crank * rows, cmask);
+                  tma_load_2d_mc(dst + PLANE_BYTES + sl, &map_lo, full, kb * FK, c * CW + (int)crank * rows, cmask);
+                }
               }
               if (++st == NSTB) { st = 0; ph ^= 1; }
             }
           }
         }
       }
+      if (pon) { prm.prof[blockIdx.x * 16 + 0] = w_bempty; prm.prof[blockIdx.x * 16 + 1] = clock64() - t_start; }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===========================================
-    if (elect_one()) {
+    // =============================== MMA issuer (leader CTA only in PAIR mode) ============
+    if (leader && elect_one()) {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, tph = 0;   // tph: per-slot phase bits of t_empty
+      long long w_afull = 0, w_bfull = 0, w_tempty = 0; const bool pon = prm.prof != nullptr;
       for (long long it = 0; it < n_iter; ++it) {
-      const long long tile = blockIdx.x + it * gridDim.x;
         for (int p = 0; p < n_pass; ++p) {
-          const int c_first = 4 * p, c_last = min(4 * p + 3, n_chunks - 1);
-          const int kb_end = 2 * c_last + 2;
+          const int c_first = NSLOT * p, c_last = min(c_first + NSLOT - 1, n_chunks - 1);
+          const int kb_end = last_kb(c_last) + 1;
           for (int kb = 0; kb < kb_end; ++kb) {
-            mbar_wait_sleep(smem_u32(&a_full[sa]), pa, 32);
+            mbar_wait_prof(smem_u32(&a_full[sa]), pa, 32, w_afull, pon);
             tc_fence_after();
             const uint32_t a_hi = smem_u32(sA + sa * STAGE_BYTES), a_lo = a_hi + PLANE_BYTES;
-            for (int c = max(c_first, kb >> 1); c <= c_last; ++c) {
-              const int slot = c & 3;
+            for (int c = max(c_first, kb >> KSH); c <= c_last; ++c) {
+              const int slot = c & (NSLOT - 1);
               if (kb == 0) {                                  // first touch of this accumulator slot
-                mbar_wait_sleep(smem_u32(&t_empty[slot]), ((tph >> slot) & 1) ^ 1, 32);
+                mbar_wait_prof(smem_u32(&t_empty[slot]), ((tph >> slot) & 1) ^ 1, 32, w_tempty, pon);
                 tph ^= (1u << slot);
                 tc_fence_after();
               }
-              mbar_wait_sleep(smem_u32(&b_full[sb]), pb, 32);
+              mbar_wait_prof(smem_u32(&b_full[sb]), pb, 32, w_bfull, pon);
               tc_fence_after();
               const uint32_t b_hi = smem_u32(sB + sb * STAGE_BYTES), b_lo = b_hi + PLANE_BYTES;
-              const uint32_t dcol = tmem_base + (uint32_t)(slot * FN);
-              if (!(prm.dbg & 1))
+              const uint32_t dcol = tmem_base + (uint32_t)(slot * CW);
+              if (!(prm.dbg & 1)) {
 #pragma unroll
-              for (int ks = 0; ks < FK / 16; ++ks) {
-                const uint64_t dah = make_sdesc(a_hi + ks * 32), dal = make_sdesc(a_lo + ks * 32);
-                const uint64_t dbh = make_sdesc(b_hi + ks * 32), dbl = make_sdesc(b_lo + ks * 32);
-                umma_bf16(dcol, dah, dbh, FAST_IDESC, (kb > 0 || ks > 0) ? 1u : 0u);
-                umma_bf16(dcol, dal, dbh, FAST_IDESC, 1u);
-                umma_bf16(dcol, dah, dbl, FAST_IDESC, 1u);
+                for (int ks = 0; ks < FK / 16; ++ks) {
+                  const uint64_t dah = make_sdesc(a_hi + ks * 32), dal = make_sdesc(a_lo + ks * 32);
+                  const uint64_t dbh = make_sdesc(b_hi + ks * 32), dbl = make_sdesc(b_lo + ks * 32);
+                  const uint32_t acc0 = (kb > 0 || ks > 0) ? 1u : 0u;
+                  if (PAIR) {
+                    umma_bf16_2sm(dcol, dah, dbh, IDESC, acc0);
+                    umma_bf16_2sm(dcol, dal, dbh, IDESC, 1u);
+                    umma_bf16_2sm(dcol, dah, dbl, IDESC, 1u);
+                  } else {
+                    umma_bf16(dcol, dah, dbh, IDESC, acc0);
+                    umma_bf16(dcol, dal, dbh, IDESC, 1u);
+                    umma_bf16(dcol, dah, dbl, IDESC, 1u);
+                  }
+                }
               }
-              if (cs == 1) umma_commit(smem_u32(&b_empty[sb])); else umma_commit_mc(smem_u32(&b_empty[sb]), cmask);
-              if (kb == 2 * c + 1) umma_commit(smem_u32(&t_full[slot]));     // chunk complete
+              if (PAIR) umma_commit_2sm(smem_u32(&b_empty[sb]));
+              else if (cs == 1) umma_commit(smem_u32(&b_empty[sb]));
+              else umma_commit_mc(smem_u32(&b_empty[sb]), cmask);
+              if (kb == last_kb(c)) {                                       // chunk complete
+                if (PAIR) umma_commit_2sm(smem_u32(&t_full[slot])); else umma_commit(smem_u32(&t_full[slot]));
+              }
               if (++sb == NSTB) { sb = 0; pb ^= 1; }
             }
-            umma_commit(smem_u32(&a_empty[sa]));
+            if (PAIR) umma_commit_2sm(smem_u32(&a_empty[sa])); else umma_commit(smem_u32(&a_empty[sa]));
             if (++sa == NSTA) { sa = 0; pa ^= 1; }
           }
         }
       }
+      if (pon) { prm.prof[blockIdx.x * 16 + 2] = w_afull; prm.prof[blockIdx.x * 16 + 3] = w_bfull; prm.prof[blockIdx.x * 16 + 4] = w_tempty; }
     }
   } else if (warp >= 4 && warp < 8) {
     // =============================== epilogue =============================================
@@ -285,22 +370,25 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
       const long long tile = blockIdx.x + it * gridDim.x;
       double ss = 0.0;
       for (int c = 0; c < n_chunks; ++c) {
-        const int slot = c & 3;
+        const int slot = c & (NSLOT - 1);
         mbar_wait_sleep(smem_u32(&t_full[slot]), (fph >> slot) & 1, 200);
         fph ^= (1u << slot);
         tc_fence_after();
         float part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int q = 0; q < FN / 32; ++q) {
+        for (int q = 0; q < CW / 32; ++q) {
           uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * FN + q * 32), v);
+          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * CW + q * 32), v);
           tmem_ld_wait();
 #pragma unroll
           for (int e = 0; e < 32; ++e) { float f = __uint_as_float(v[e]); part[e & 3] = fmaf(f, f, part[e & 3]); }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&t_empty[slot]));
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&t_empty[slot]), 0));
+          else mbar_arrive(smem_u32(&t_empty[slot]));
+        }
         ss += (double)((part[0] + part[1]) + (part[2] + part[3]));
       }
       const long long cg = tile * FM + row;
@@ -323,6 +411,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     constexpr int XT_STRIDE = (DP + 1) * FK;
     uint32_t sa = 0, pa = 0;
     int xbuf = 0;
+    long long w_aempty = 0, w_bar = 0; const bool pon = prm.prof != nullptr;
     // train-slice loader: 16 float4 per row, 16 rows per sweep; rows < DP are NEGATED coords, row DP = alpha
     const int ld_j = gt >> 4, ld_o = (gt & 15) * 4;
     constexpr int LD_SWEEPS = (DP + 1 + 15) / 16;
@@ -352,8 +441,8 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
       asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
       float mu_acc[4] = {0.f, 0.f, 0.f, 0.f};
       for (int p = 0; p < n_pass; ++p) {
-        const int c_last = min(4 * p + 3, n_chunks - 1);
-        const int kb_end = 2 * c_last + 2;
+        const int c_last = min(NSLOT * p + NSLOT - 1, n_chunks - 1);
+        const int kb_end = last_kb(c_last) + 1;
         const bool do_mu = (p == n_pass - 1);
         for (int kb = 0; kb < kb_end; ++kb) {
           const int kb_next = (kb + 1 < kb_end) ? kb + 1 : 0;
@@ -394,7 +483,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             }
             const float4 al0 = *(const float4 *)(xs + DP * FK);
             const float4 al1 = *(const float4 *)(xs + DP * FK + 4);
-            if (rb == 0) mbar_wait_sleep(smem_u32(&a_empty[sa]), pa ^ 1, 32);   // stage released by the MMA
+            if (rb == 0) mbar_wait_prof(smem_u32(&a_empty[sa]), pa ^ 1, 32, w_aempty, pon);   // stage released by the MMA
 #pragma unroll
             for (int rr = 0; rr < R; ++rr) {
               float2 kv[4];
@@ -447,7 +536,10 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&a_full[sa]));
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&a_full[sa]), 0));   // the leader's MMA consumes both halves
+            else mbar_arrive(smem_u32(&a_full[sa]));
+          }
           if (++sa == NSTA) { sa = 0; pa ^= 1; }
           // install the prefetched slice in the other buffer
           float *xn = xt + (xbuf ^ 1) * XT_STRIDE;
@@ -456,10 +548,13 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             const int jj = ld_j + 16 * sw;
             if (jj <= DP) *(float4 *)(xn + jj * FK + ld_o) = nxt[sw];
           }
-          asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
+          { long long t0 = pon ? clock64() : 0;
+            asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
+            if (pon) w_bar += clock64() - t0; }
           xbuf ^= 1;
         }
       }
+      if (pon && lane == 0) { prm.prof[blockIdx.x * 16 + 5 + 0] = w_aempty; if (q == 0) prm.prof[blockIdx.x * 16 + 6] = w_bar; if (q == 7) prm.prof[blockIdx.x * 16 + 7] = w_bar; }
       // mean: one partial sum per (chunk warp, row)
 #pragma unroll
       for (int r4 = 0; r4 < 4; ++r4) mu_sm[q * FM + lane + 32 * r4] = mu_acc[r4];
@@ -481,7 +576,8 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
   __syncthreads();
   if (cs > 1) cluster_sync_all();          // nobody exits while a peer may still signal / multicast to it
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u));
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u));
   }
 }
 
@@ -518,14 +614,14 @@ static int make_b_map(CUtensorMap *map, const void *base, int n_pad, int cs) {
 
 int ombo_fast_path_built() { return 1; }
 
-template <int DP, int R>
+template <int DP, int R, bool PAIR>
 static int launch_fast(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensorMap &map_lo, const FastParams &prm,
                        int grid, int cs, cudaStream_t s) {
   const size_t smem = (size_t)(NSTA + NSTB) * STAGE_BYTES + (size_t)DP * FM * 4 + 2 * (size_t)(DP + 1) * FK * 4 +
                       GEN_WARPS * FM * 4 + 16 + (2 * NSTA + 2 * NSTB + 8) * 8 + 16 + 1024;
   static bool attr = false;
   if (!attr) {
-    OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast<DP, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast<DP, R, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   ProfScope prof(ctx, s);
@@ -539,7 +635,7 @@ static int launch_fast(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensorM
   at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  OMBO_CUDA(cudaLaunchKernelEx(&cfg, k_posterior_fast<DP, R>, map_hi, map_lo, prm));
+  OMBO_CUDA(cudaLaunchKernelEx(&cfg, k_posterior_fast<DP, R, PAIR>, map_hi, map_lo, prm));
   return OMBO_OK;
 }
 
@@ -550,32 +646,57 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
     ombo_set_error("fast precision mode supports d <= 24 (got %d); use OMBO_PREC_FP64", gp.d);
     return OMBO_ERR_UNSUPPORTED;
   }
-  int cs = 2;                                  // CTAs per cluster sharing each multicast B tile
-  { const char *e = getenv("OMBO_FAST_CLUSTER"); if (e) cs = atoi(e); }
-  if (cs != 1 && cs != 2 && cs != 4) cs = 2;
+  // default: single-CTA UMMA (M = 128, N = 128): measured faster end to end (round 1: 1.5e8 vs 1.3e8
+  // cand/s) because the pair variant couples two CTAs' K1 generators to one MMA stream.
+  // OMBO_FAST_MODE=2 selects the cta_group::2 pair variant, OMBO_FAST_CLUSTER the multicast cluster
+  // size of the single-CTA variant (both for experiments).
   long long tiles = (m + FM - 1) / FM;
-  if (tiles < cs) cs = 1;
+  bool pair = false;
+  int cs = 1;
+  { const char *e = getenv("OMBO_FAST_MODE"); if (e && atoi(e) == 2) pair = true; }
+  if (!pair) { const char *e = getenv("OMBO_FAST_CLUSTER"); if (e) cs = atoi(e); if (cs != 1 && cs != 2 && cs != 4) cs = 1; if (tiles < cs) cs = 1; }
+  if (pair) cs = 2;
   CUtensorMap map_hi, map_lo;
-  int rc = make_b_map(&map_hi, gp.bhi, gp.n_pad, cs);
+  int rc = make_b_map(&map_hi, gp.bhi, gp.n_pad, pair ? 1 : cs);
   if (rc) return rc;
-  rc = make_b_map(&map_lo, gp.blo, gp.n_pad, cs);
+  rc = make_b_map(&map_lo, gp.blo, gp.n_pad, pair ? 1 : cs);
   if (rc) return rc;
   FastParams prm;
   prm.gp = gp; prm.pool = pool; prm.m = m; prm.mu_out = mu; prm.var_out = var;
   { const char *e = getenv("OMBO_FAST_DBG"); prm.dbg = e ? atoi(e) : 0; }
+  static long long *prof_dev = nullptr;
+  const bool want_prof = getenv("OMBO_FAST_PROFILE") != nullptr;
+  if (want_prof && !prof_dev) OMBO_CUDA(cudaMalloc(&prof_dev, 16 * 256 * sizeof(long long)));
+  prm.prof = want_prof ? prof_dev : nullptr;
+  if (want_prof) OMBO_CUDA(cudaMemsetAsync(prof_dev, 0, 16 * 256 * sizeof(long long), s));
   int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
-  grid = grid / cs * cs;                       // whole clusters; the uniform iteration count covers the remainder
+  grid = (grid + cs - 1) / cs * cs;            // whole clusters; surplus CTAs run a dummy tile
+  if (grid > ctx->num_sms) grid = ctx->num_sms / cs * cs;
   const int d = gp.d;
-  if (d <= 2) rc = launch_fast<2, 4>(ctx, map_hi, map_lo, prm, grid, cs, s);
-  else if (d <= 4) rc = launch_fast<4, 4>(ctx, map_hi, map_lo, prm, grid, cs, s);
-  else if (d <= 6) rc = launch_fast<6, 4>(ctx, map_hi, map_lo, prm, grid, cs, s);
-  else if (d <= 8) rc = launch_fast<8, 4>(ctx, map_hi, map_lo, prm, grid, cs, s);
-  else if (d <= 10) rc = launch_fast<10, 4>(ctx, map_hi, map_lo, prm, grid, cs, s);
-  else if (d <= 12) rc = launch_fast<12, 4>(ctx, map_hi, map_lo, prm, grid, cs, s);
-  else if (d <= 16) rc = launch_fast<16, 2>(ctx, map_hi, map_lo, prm, grid, cs, s);
-  else rc = launch_fast<24, 2>(ctx, map_hi, map_lo, prm, grid, cs, s);
+#define FAST_DISPATCH(DPV, RV)                                                                  \
+  rc = pair ? launch_fast<DPV, RV, true>(ctx, map_hi, map_lo, prm, grid, cs, s)                   \
+            : launch_fast<DPV, RV, false>(ctx, map_hi, map_lo, prm, grid, cs, s)
+  if (d <= 2) { FAST_DISPATCH(2, 4); }
+  else if (d <= 4) { FAST_DISPATCH(4, 4); }
+  else if (d <= 6) { FAST_DISPATCH(6, 4); }
+  else if (d <= 8) { FAST_DISPATCH(8, 4); }
+  else if (d <= 10) { FAST_DISPATCH(10, 4); }
+  else if (d <= 12) { FAST_DISPATCH(12, 4); }
+  else if (d <= 16) { FAST_DISPATCH(16, 2); }
+  else { FAST_DISPATCH(24, 2); }
+#undef FAST_DISPATCH
   if (rc) return rc;
   ctx->launches += 1;
   OMBO_CUDA(cudaGetLastError());
+  if (want_prof) {
+    static long long h[16 * 256];
+    OMBO_CUDA(cudaStreamSynchronize(s));
+    OMBO_CUDA(cudaMemcpy(h, prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    double a[8] = {0};
+    for (int b = 0; b < grid; ++b) for (int k = 0; k < 8; ++k) a[k] += (double)h[b * 16 + k] / grid;
+    fprintf(stderr, "[fast prof] per-CTA cycles: tma.wait_b_empty %.0f / tma.total %.0f | mma.wait_a_full %.0f wait_b_full %.0f "
+            "wait_t_empty %.0f | gen.wait_a_empty %.0f gen.bar(w0) %.0f gen.bar(w7) %.0f  (tiles/CTA %.1f)\n",
+            a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], (double)tiles / grid);
+  }
   return OMBO_OK;
 }
