@@ -1,0 +1,114 @@
+"""Shared outer-loop plumbing of the re-hosted optimisers.
+
+The BO outer loops (LHS init -> per iteration: bounds, hypervolume, GP fit, acquisition,
+evaluate, append) are host orchestration and are out of scope for kernels (SURVEY.md section 2,
+rows 3-7); they are re-hosted thinly so `.solve()` keeps working.  What changes is the seam
+`_get_proposed*`: where the reference calls `scipy.optimize.differential_evolution(obj, bounds)`
+(optimisers.py:87,118,366; cparego.py:94,544; emo.py:240) or a 20-member / 1000-generation EA
+(parego.py:242-270, keep.py:260-292) that evaluates the acquisition one x at a time, this path
+scores a pool of `n_candidates` points in one fused GPU pass and takes the arg-max.
+
+Additive knobs (reference defaults untouched): n_candidates, precision {"auto","fp64","fast"},
+semantics {"reference","exact"}, device, seed, fit (callable or fixed hyper-parameters).
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from .. import host_prep
+from ..acquisition import CandidatePool, propose
+from ..fit import fit_hyperparameters
+from ..gp import GPModel
+
+
+class PoolOptimiserBase:
+    def __init__(self, test_problem, ideal_point=None, max_point=None, n_candidates=1 << 16, precision="auto",
+                 semantics="reference", device="cuda:0", seed=None, hyperparameters=None, max_f_eval=1000):
+        self.test_problem = test_problem
+        self.max_point = max_point
+        self.ideal_point = ideal_point
+        self.n_vars = test_problem.n_var
+        self.n_obj = test_problem.n_obj
+        self.upper = test_problem.xu
+        self.lower = test_problem.xl
+        self.is_ideal_known = ideal_point is not None
+        self.is_max_known = max_point is not None
+        # --- B200-path knobs ---
+        self.n_candidates = int(n_candidates)
+        self.precision = precision
+        self.semantics = semantics
+        self.device = device
+        self.rng = np.random.default_rng(seed)
+        self.hyperparameters = hyperparameters      # (lengthscale, variance) to skip the fit (parity tests)
+        self.max_f_eval = max_f_eval
+        self.timings = []
+
+    # ---- problem access ------------------------------------------------------------------------
+    def _objective_function(self, problem, x):
+        return problem.evaluate(x)
+
+    def _constraint_function(self, problem, x):
+        return problem.evaluate_constraints(x)
+
+    def _initial_design(self, n_init_samples):
+        ranges = list(zip(self.test_problem.xl, self.test_problem.xu))
+        X = host_prep.latin_hypercube(n_init_samples, ranges, self.rng)
+        Y = np.asarray([self._objective_function(self.test_problem, x) for x in X])
+        return X, Y
+
+    # ---- bounds bookkeeping (optimisers.py:190-213 and its copies) ---------------------------
+    def _update_bounds(self, ysample, scalarisation=None):
+        changed = False
+        if not self.is_max_known:
+            self.max_point = ysample.max(axis=0)
+            changed = True
+        if not self.is_ideal_known:
+            self.ideal_point = ysample.min(axis=0)
+            changed = True
+        if changed and scalarisation is not None:
+            scalarisation.set_bounds(self.ideal_point, self.max_point)
+
+    def _hypervolume(self, ysample, ref_point=None):
+        return host_prep.hypervolume(ysample, self.max_point if ref_point is None else ref_point)
+
+    # ---- surrogate ---------------------------------------------------------------------------------
+    def _fit_model(self, X, y):
+        t0 = time.perf_counter()
+        if self.hyperparameters is not None:
+            ell, sf2 = self.hyperparameters
+        else:
+            ell, sf2 = fit_hyperparameters(X, y, max_f_eval=self.max_f_eval)
+        t1 = time.perf_counter()
+        model = GPModel(X, y, ell, sf2, noise=0.0, device=self.device)
+        self._t_fit = getattr(self, "_t_fit", 0.0) + (t1 - t0)
+        self._t_refresh = getattr(self, "_t_refresh", 0.0) + (time.perf_counter() - t1)
+        return model
+
+    def _precision_for(self, models):
+        if self.precision != "auto":
+            return self.precision
+        from .. import _cabi
+        # small / ill-conditioned GPs: FP64 is cheap and the fast mode's 1e-3 tolerance is not met near
+        # training points (DESIGN.md "fast mode validity")
+        n = max(m.n for m in models)
+        d = models[0].d
+        return "fast" if (_cabi.fast_path_available() and n > 256 and d <= 24) else "fp64"
+
+    # ---- the seam: pool scoring + arg-max instead of DE / EA ---------------------------------
+    def _propose(self, models, spec):
+        t0 = time.perf_counter()
+        pool = CandidatePool.counter(self.n_candidates, self.test_problem.xl, self.test_problem.xu,
+                                     seed=int(self.rng.integers(1, 2 ** 62)))
+        x, neg_value, index = propose(models, spec, pool, precision=self._precision_for(models))
+        self.timings.append(dict(fit_s=getattr(self, "_t_fit", 0.0), refresh_s=getattr(self, "_t_refresh", 0.0),
+                                 score_s=time.perf_counter() - t0, n_candidates=self.n_candidates))
+        self._t_fit = self._t_refresh = 0.0
+        return x, neg_value
+
+    # ---- result ------------------------------------------------------------------------------------
+    @staticmethod
+    def _pareto_members(ysample):
+        mask = host_prep.pareto_mask(ysample) if len(ysample) > 1 else np.ones(len(ysample), bool)
+        return mask

@@ -1,0 +1,149 @@
+"""GPU: the re-hosted optimiser surface (`.solve()` of the six classes the reference exposes) runs
+end to end on the pool-scoring path, and the sharded multi-GPU entry agrees with the single-GPU one."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+import optimobo_b200 as ob  # noqa: E402
+import optimobo_b200.scalarisations as sc  # noqa: E402
+from optimobo_b200.algorithms import (EMO, KEEP, MonoSurrogateOptimiser, MultiSurrogateOptimiser, ParEGO,  # noqa: E402
+                                      ParEGO_C1, ParEGO_C2)
+from optimobo_b200.problem import ElementwiseProblem, Problem  # noqa: E402
+
+
+class MyProblem(ElementwiseProblem):     # README example 1 (BASELINE config 1)
+    def __init__(self):
+        super().__init__(n_var=2, n_obj=2, xl=np.array([-2, -2]), xu=np.array([2, 2]))
+
+    def _evaluate(self, x, out, *args, **kwargs):
+        out["F"] = [100 * (x[0] ** 2 + x[1] ** 2), (x[0] - 1) ** 2 + x[1] ** 2]
+
+
+class BNH(Problem):                      # README example 2 (BASELINE config 3)
+    def __init__(self):
+        super().__init__(n_var=2, n_obj=2, n_ieq_constr=2, vtype=float)
+        self.xl = np.zeros(self.n_var)
+        self.xu = np.array([5.0, 3.0])
+
+    def _evaluate(self, x, out, *args, **kwargs):
+        out["F"] = [4 * x[:, 0] ** 2 + 4 * x[:, 1] ** 2, (x[:, 0] - 5) ** 2 + (x[:, 1] - 5) ** 2]
+
+    def _evaluate_constraints(self, x, out, *args, **kwargs):
+        out["G"] = [(1 / 25) * ((x[:, 0] - 5) ** 2 + x[:, 1] ** 2 - 25),
+                    -1 / 7.7 * ((x[:, 0] - 8) ** 2 + (x[:, 1] + 3) ** 2 - 7.7)]
+
+
+class DTLZ2(Problem):
+    def __init__(self, n_var=6, n_obj=3):
+        super().__init__(n_var=n_var, n_obj=n_obj, xl=np.zeros(n_var), xu=np.ones(n_var))
+
+    def _evaluate(self, x, out, *args, **kwargs):
+        g = ((x[:, 2:] - 0.5) ** 2).sum(1)
+        a, b = 0.5 * np.pi * x[:, 0], 0.5 * np.pi * x[:, 1]
+        out["F"] = [(1 + g) * np.cos(a) * np.cos(b), (1 + g) * np.cos(a) * np.sin(b), (1 + g) * np.sin(a)]
+
+
+KW = dict(n_candidates=1 << 14, seed=0, device="cuda:0", max_f_eval=200)
+
+
+def _check(res, n_init, budget, n_obj=2):
+    assert res.ysample.shape == (n_init + budget, n_obj) and res.Xsample.shape[0] == n_init + budget
+    assert len(res.hypervolume_convergence) >= 1 and len(res.pf_approx) >= 1
+    assert res.pf_inputs.shape[0] == res.pf_approx.shape[0]
+    assert np.all(np.isfinite(res.ysample))
+    assert len(res.timings) >= 1 and res.timings[0]["score_s"] > 0
+
+
+def test_multisurrogate_readme_tchebicheff_improves_hypervolume():
+    opt = MultiSurrogateOptimiser(MyProblem(), [0, 0], [700, 12], **KW)
+    res = opt.solve(budget=12, n_init_samples=20, sample_exponent=3, acquisition_func=sc.Tchebicheff([0, 0], [700, 12]))
+    _check(res, 20, 12)
+    hv = res.hypervolume_convergence
+    assert hv[-1] >= hv[0] and all(b >= a - 1e-9 for a, b in zip(hv, hv[1:]))
+    final = ob.host_prep.hypervolume(res.ysample, [700, 12])
+    assert final > hv[0]
+
+
+def test_multisurrogate_default_ehvi_and_unknown_bounds():
+    res = MultiSurrogateOptimiser(MyProblem(), **KW).solve(budget=4, n_init_samples=10)
+    _check(res, 10, 4)
+    res = MultiSurrogateOptimiser(MyProblem(), [0, 0], [700, 12], semantics="exact", **KW).solve(budget=4, n_init_samples=10)
+    _check(res, 10, 4)
+
+
+def test_multisurrogate_three_objectives_ehvi3d():
+    res = MultiSurrogateOptimiser(DTLZ2(), [0, 0, 0], [2.5, 2.5, 2.5], **KW).solve(budget=3, n_init_samples=12)
+    _check(res, 12, 3, n_obj=3)
+
+
+def test_monosurrogate_parego_keep_emo():
+    agg = sc.AugmentedTchebicheff([0, 0], [700, 12])
+    _check(MonoSurrogateOptimiser(MyProblem(), [0, 0], [700, 12], **KW).solve(agg, budget=4, n_init_samples=8), 8, 4)
+    _check(ParEGO(MyProblem(), [0, 0], [700, 12], **KW).solve(sc.Tchebicheff([0, 0], [700, 12]), budget=4, n_init_samples=8), 8, 4)
+    _check(KEEP(MyProblem(), [0, 0], [700, 12], **KW).solve(sc.PBI([0, 0], [700, 12]), budget=3, n_init_samples=8), 8, 3)
+    _check(EMO(MyProblem(), [0, 0], [700, 12], **KW).solve(budget=4, n_init_samples=8), 8, 4)
+
+
+def test_constrained_parego_bnh():
+    for cls in (ParEGO_C1, ParEGO_C2):
+        res = cls(BNH(), [0, 0], [150, 60], **KW).solve(sc.Tchebicheff([0, 0], [150, 60]), budget=11, n_init_samples=12)
+        assert res.ysample.shape == (12 + 11, 2) and res.gsample.shape == (23, 2)
+        assert len(res.y_feasible) + len(res.y_infeasible) == 23
+        assert np.all(np.any(res.gsample > 0, axis=1) == np.r_[[False] * 0, np.any(res.gsample > 0, axis=1)])
+
+
+def test_reference_acquisition_callables_run_unmodified_on_gpmodel(golden):
+    """The GPy-shaped surface: the ORACLE's per-candidate restatement of the reference call pattern
+    (predict one x at a time) evaluated on GPModel equals the batched GPU acquisition."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(0)
+    X = rng.random((60, 3))
+    Y = np.column_stack([X[:, 0], 1 + X[:, 1:].sum(1) - np.sqrt(X[:, 0])])
+    models = [ob.GPModel(X, Y[:, i], 0.6 * np.ones(3), 1.0 + i, device="cuda:0") for i in range(2)]
+    cache = golden["acq_in_cache2"]
+    PF, r = ob.host_prep.calc_pf(Y), Y.max(0)
+    Xc = rng.random((40, 3))
+    batched = ob.EHVI(Xc, models, r, PF, cache)
+    one_at_a_time = []
+    for x in Xc:                                   # util_functions.py:154-167 call pattern
+        preds = [m.predict(np.asarray([x])) for m in models]
+        mu = np.array([[p[0][0][0] for p in preds]]); var = np.array([[p[1][0][0] for p in preds]])
+        one_at_a_time.append(O.ehvi_batched(mu[:, 0], mu[:, 1], var[:, 0], var[:, 1], PF, r, cache)[0])
+    np.testing.assert_allclose(batched, one_at_a_time, rtol=1e-6, atol=1e-9 * np.abs(batched).max())
+
+
+def test_score_sharded_single_process_matches_score():
+    from optimobo_b200.distributed import score_sharded
+    rng = np.random.default_rng(0)
+    X = rng.random((128, 5)); y = np.sin(X.sum(1))
+    gp = ob.GPModel(X, y, 0.8 * np.ones(5), 1.0, device="cuda:0")
+    pool = ob.CandidatePool.counter(50000, np.zeros(5), np.ones(5), seed=3)
+    v, i = score_sharded([gp], ob.spec_ei(y.min(), 0.0), pool)
+    ref = ob.score([gp], ob.spec_ei(y.min(), 0.0), pool)
+    assert (v, i) == (ref.best_value, ref.best_index)
+    # emulate 4 ranks by hand: shard bests combined through the packed key == global best
+    from optimobo_b200.distributed import pack_key_host, unpack_key
+    keys = []
+    for rnk in range(4):
+        r = ob.score([gp], ob.spec_ei(y.min(), 0.0), pool.shard(rnk, 4))
+        keys.append(pack_key_host(r.best_value, r.best_index))
+    assert unpack_key(max(keys))[1] == ref.best_index
+
+
+def test_nccl_two_ranks_agree_with_single_gpu():
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611",
+                          os.path.join(root, "scripts", "check_multigpu.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "multi-GPU check ok" in out.stdout
