@@ -192,9 +192,25 @@ static int score_pass(ombo_ctx *ctx, const ombo_gp *gps, int n_gp, const ombo_po
   }
   for (int g = 0; g < n_gp; ++g) {
     GpDev gd = gp_dev_view(gps[g]);
+    // K2 is skipped for GPs whose variance nothing reads (the caller did not ask for the posterior and
+    // the acquisition ignores it): reference-semantics EHVI / EHVI_3D / expected decomposition scale
+    // every objective by model 0's variance (util_functions.py:233), KEEP reads only the Pareto
+    // model's mean (keep.py:149)
+    bool want_var = true;
+    if (!out_var) {
+      const bool ref = acq->semantics == OMBO_SEM_REFERENCE;
+      switch (acq->kind) {
+        case OMBO_ACQ_EHVI2D: case OMBO_ACQ_EHVI3D: case OMBO_ACQ_EXPECTED_DECOMP:
+          want_var = ref ? (g == 0) : (g < (acq->kind == OMBO_ACQ_EHVI2D ? 2 : acq->n_obj)); break;
+        case OMBO_ACQ_EI: want_var = (g == 0); break;
+        case OMBO_ACQ_PARETO_EI: want_var = (g == 1); break;
+        case OMBO_ACQ_HV_POI: want_var = (g < 2); break;
+        default: want_var = true;
+      }
+    }
     int rc = (precision == OMBO_PREC_FP64)
-                 ? ombo_posterior_fp64(ctx, gd, pd, count, mu + (size_t)g * ld, var + (size_t)g * ld, s)
-                 : ombo_posterior_fast(ctx, gd, pd, count, mu + (size_t)g * ld, var + (size_t)g * ld, s);
+                 ? ombo_posterior_fp64(ctx, gd, pd, count, mu + (size_t)g * ld, var + (size_t)g * ld, want_var, s)
+                 : ombo_posterior_fast(ctx, gd, pd, count, mu + (size_t)g * ld, var + (size_t)g * ld, want_var, s);
     if (rc) return rc;
   }
   if (acq->kind != OMBO_ACQ_NONE)

@@ -139,9 +139,9 @@ struct PoolDev {
 // ---- internal entry points (one per .cu) ------------------------------------------------
 int ombo_refresh_impl(ombo_ctx *ctx, const ombo_gp_spec *spec, void *state, cudaStream_t s);
 int ombo_posterior_fp64(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, long long m,
-                        double *mu, double *var, cudaStream_t s);
+                        double *mu, double *var, bool want_var, cudaStream_t s);
 int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, long long m,
-                        double *mu, double *var, cudaStream_t s);
+                        double *mu, double *var, bool want_var, cudaStream_t s);
 int ombo_fast_path_built();
 int ombo_acquire(ombo_ctx *ctx, const ombo_acq *acq, int n_gp, const double *mu, const double *var,
                  long long m, long long ld, long long index_base, double *out_acq,

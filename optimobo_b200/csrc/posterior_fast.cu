@@ -195,6 +195,7 @@ struct FastParams {
   long long m;
   double *mu_out, *var_out;
   long long *prof;   // optional per-CTA wait-cycle counters (timing experiments)
+  int mean_only;     // 1: this GP's variance is not read by the acquisition -> K1 + mean only, no MMA
   int dbg;   // bit 0: skip the MMAs, bit 1: skip the K1 math (timing experiments only; results are garbage)
 };
 
@@ -267,9 +268,10 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  const bool mo = prm.mean_only != 0;
   if (warp == 0) {
     // =============================== TMA producer (B tiles) ===============================
-    if (elect_one()) {
+    if (!mo && elect_one()) {
       uint32_t st = 0, ph = 0;
       long long w_bempty = 0; const bool pon = prm.prof != nullptr; const long long t_start = clock64();
       for (long long it = 0; it < n_iter; ++it) {
@@ -307,7 +309,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (leader CTA only in PAIR mode) ============
-    if (leader && elect_one()) {
+    if (!mo && leader && elect_one()) {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, tph = 0;   // tph: per-slot phase bits of t_empty
       long long w_afull = 0, w_bfull = 0, w_tempty = 0; const bool pon = prm.prof != nullptr;
       for (long long it = 0; it < n_iter; ++it) {
@@ -366,7 +368,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     const int quad = warp - 4;
     const int row = quad * 32 + lane;
     uint32_t fph = 0;                                        // per-slot phase bits of t_full
-    for (long long it = 0; it < n_iter; ++it) {
+    for (long long it = 0; it < (mo ? 0 : n_iter); ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
       double ss = 0.0;
       for (int c = 0; c < n_chunks; ++c) {
@@ -440,10 +442,10 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
       }
       asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
       float mu_acc[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int p = 0; p < n_pass; ++p) {
+      for (int p = 0; p < (mo ? 1 : n_pass); ++p) {
         const int c_last = min(NSLOT * p + NSLOT - 1, n_chunks - 1);
-        const int kb_end = last_kb(c_last) + 1;
-        const bool do_mu = (p == n_pass - 1);
+        const int kb_end = mo ? nkb : last_kb(c_last) + 1;
+        const bool do_mu = mo || (p == n_pass - 1);
         for (int kb = 0; kb < kb_end; ++kb) {
           const int kb_next = (kb + 1 < kb_end) ? kb + 1 : 0;
           float4 nxt[LD_SWEEPS];
@@ -483,7 +485,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             }
             const float4 al0 = *(const float4 *)(xs + DP * FK);
             const float4 al1 = *(const float4 *)(xs + DP * FK + 4);
-            if (rb == 0) mbar_wait_prof(smem_u32(&a_empty[sa]), pa ^ 1, 32, w_aempty, pon);   // stage released by the MMA
+            if (rb == 0 && !mo) mbar_wait_prof(smem_u32(&a_empty[sa]), pa ^ 1, 32, w_aempty, pon);   // stage released by the MMA
 #pragma unroll
             for (int rr = 0; rr < R; ++rr) {
               float2 kv[4];
@@ -516,6 +518,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                 m2 = __ffma2_rn(kv[3], make_float2(al1.z, al1.w), m2);
                 mu_acc[R * rb + rr] += m2.x + m2.y;
               }
+              if (!mo) {
               uint32_t hi[4], lo[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -532,11 +535,12 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
               const uint32_t off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((q ^ (row & 7)) & 7) << 4));
               *(uint4 *)(st_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *(uint4 *)(st_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
             }
           }
-          fence_proxy_async_smem();
+          if (!mo) fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (lane == 0 && !mo) {
             if (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&a_full[sa]), 0));   // the leader's MMA consumes both halves
             else mbar_arrive(smem_u32(&a_full[sa]));
           }
@@ -566,6 +570,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
 #pragma unroll
           for (int w = 0; w < GEN_WARPS; ++w) acc += mu_sm[w * FM + gt];
           prm.mu_out[cg] = (double)acc;
+          if (mo) prm.var_out[cg] = nan("");
         }
       }
     }
@@ -640,7 +645,7 @@ static int launch_fast(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensorM
 }
 
 int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, long long m, double *mu, double *var,
-                        cudaStream_t s) {
+                        bool want_var, cudaStream_t s) {
   if (m <= 0) return OMBO_OK;
   if (gp.d > 24) {
     ombo_set_error("fast precision mode supports d <= 24 (got %d); use OMBO_PREC_FP64", gp.d);
@@ -662,7 +667,7 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
   rc = make_b_map(&map_lo, gp.blo, gp.n_pad, pair ? 1 : cs);
   if (rc) return rc;
   FastParams prm;
-  prm.gp = gp; prm.pool = pool; prm.m = m; prm.mu_out = mu; prm.var_out = var;
+  prm.gp = gp; prm.pool = pool; prm.m = m; prm.mu_out = mu; prm.var_out = var; prm.mean_only = want_var ? 0 : 1;
   { const char *e = getenv("OMBO_FAST_DBG"); prm.dbg = e ? atoi(e) : 0; }
   static long long *prof_dev = nullptr;
   const bool want_prof = getenv("OMBO_FAST_PROFILE") != nullptr;

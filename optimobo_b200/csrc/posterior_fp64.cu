@@ -49,7 +49,7 @@ extern __shared__ __align__(16) unsigned char smem_raw[];
 
 __global__ void __launch_bounds__(256, 2)
 k_posterior_fp64(GpDev gp, PoolDev pool, long long m, double *__restrict__ scratch_all,
-                 double *__restrict__ mu_out, double *__restrict__ var_out) {
+                 double *__restrict__ mu_out, double *__restrict__ var_out, int want_var) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = gp.d, n = gp.n, np = gp.n_pad;
   double *scratch = scratch_all + (size_t)blockIdx.x * TM * np;
@@ -100,7 +100,7 @@ k_posterior_fp64(GpDev gp, PoolDev pool, long long m, double *__restrict__ scrat
         for (int q = 0; q < 4; ++q) {
           int i = i0 + lane + 32 * q;
           double k = (i < n) ? kstar_of_r2(r2[q], gp.sigma_f2, gp.kernel) : 0.0;
-          scratch[(size_t)c * np + i] = k;
+          if (want_var) scratch[(size_t)c * np + i] = k;
           mu_part += k * al[q];
         }
         for (int o = 16; o; o >>= 1) mu_part += __shfl_xor_sync(0xffffffffu, mu_part, o);
@@ -114,7 +114,7 @@ k_posterior_fp64(GpDev gp, PoolDev pool, long long m, double *__restrict__ scrat
     const int wm = warp >> 2, wn = warp & 3;
     const int g8 = lane >> 2, t4 = lane & 3;
     double ss[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int j0 = 0; j0 < np; j0 += NC) {
+    for (int j0 = 0; j0 < (want_var ? np : 0); j0 += NC) {
       if (j0 >= n) break;                       // remaining rows of Linv are padding (zero)
       double acc[4][4][2];
 #pragma unroll
@@ -174,14 +174,14 @@ k_posterior_fp64(GpDev gp, PoolDev pool, long long m, double *__restrict__ scrat
         double v = gp.sigma_f2 - (((red_ss[0][tid] + red_ss[1][tid]) + red_ss[2][tid]) + red_ss[3][tid]);
         v = fmax(v, gp.var_floor) + gp.sigma_n2;
         mu_out[cg] = red_mu[tid];
-        var_out[cg] = v;
+        var_out[cg] = want_var ? v : nan("");
       }
     }
   }
 }
 
 int ombo_posterior_fp64(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, long long m, double *mu,
-                        double *var, cudaStream_t s) {
+                        double *var, bool want_var, cudaStream_t s) {
   if (m <= 0) return OMBO_OK;
   const size_t smem_b = (size_t)(2 * TM * SROW + 2 * NC * SROW) * 8;
   const size_t smem_a = (size_t)(TM * gp.d + gp.d * TCH) * 8;
@@ -198,7 +198,7 @@ int ombo_posterior_fp64(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
   if (rc) return rc;
   {
     ProfScope prof(ctx, s);
-    k_posterior_fp64<<<grid, 256, smem, s>>>(gp, pool, m, (double *)ctx->ws_scratch, mu, var);
+    k_posterior_fp64<<<grid, 256, smem, s>>>(gp, pool, m, (double *)ctx->ws_scratch, mu, var, want_var ? 1 : 0);
   }
   ctx->launches += 1;
   OMBO_CUDA(cudaGetLastError());
