@@ -95,7 +95,7 @@ enum { OMBO_FIELD_L = 0,      /* (n_pad, n_pad) f64 lower Cholesky factor       
        OMBO_FIELD_STATUS = 4, /* (4,) i32: [0] = first non-PD pivot row + 1, 0 if PD       */
        OMBO_FIELD_BHI = 5,    /* (n_pad, n_pad) bf16, hi plane of sigma_f2 * Linv          */
        OMBO_FIELD_BLO = 6,    /* (n_pad, n_pad) bf16, lo plane                             */
-       OMBO_FIELD_XS32 = 7,   /* (32, n_pad) f32 scaled training inputs (fast path)        */
+       OMBO_FIELD_XS32 = 7,   /* (32, n_pad) f32 centred scaled training inputs (fast path) */
        OMBO_FIELD_ALPHA32 = 8 /* (n_pad,) f32 alpha * sigma_f2                              */
 };
 

@@ -71,7 +71,7 @@ int ombo_ws_reserve(void **p, size_t *cur, size_t want);
 struct GpLayout {
   int n, d, n_pad;
   size_t off_L, off_Linv, off_alpha, off_xs, off_status, off_dinv, off_tmp, off_inv_ell;
-  size_t off_bhi, off_blo, off_xs32, off_alpha32;
+  size_t off_bhi, off_blo, off_xs32, off_alpha32, off_center, off_b2;
   size_t bytes;
 };
 
@@ -94,6 +94,8 @@ static inline GpLayout gp_layout(int n, int d) {
   L.off_blo = take(np * np * 2);
   L.off_xs32 = take(np * 32 * 4);
   L.off_alpha32 = take(np * 4);
+  L.off_center = take((size_t)OMBO_MAX_DIM * 8);
+  L.off_b2 = take(np * 4);
   L.bytes = off;
   return L;
 }
@@ -107,7 +109,8 @@ struct GpDev {
   const double *Linv;     // (n_pad, n_pad)
   const double *alpha;    // (n_pad)
   const __nv_bfloat16 *bhi, *blo;
-  const float *xs32, *alpha32;
+  const float *xs32, *alpha32, *b2_32;   // fast path: centred scaled inputs, sigma_f2*alpha, |xs32_i|^2
+  const double *center;                  // (d) per-dimension mean of the training inputs
 };
 
 static inline GpDev gp_dev_view(const ombo_gp &g) {
@@ -124,6 +127,8 @@ static inline GpDev gp_dev_view(const ombo_gp &g) {
   v.blo = (const __nv_bfloat16 *)(b + L.off_blo);
   v.xs32 = (const float *)(b + L.off_xs32);
   v.alpha32 = (const float *)(b + L.off_alpha32);
+  v.b2_32 = (const float *)(b + L.off_b2);
+  v.center = (const double *)(b + L.off_center);
   return v;
 }
 

@@ -14,19 +14,41 @@
 #define LDS (NB + 1)
 
 // ------------------------------------------------------------------------------------------
+// per-dimension mean of the training inputs (fixed-order tree: bit-reproducible)
+__global__ void __launch_bounds__(256) k_center(const double *__restrict__ X, int n, int d, double *__restrict__ center) {
+  __shared__ double part[256];
+  const int j = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) s += X[(size_t)i * d + j];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) center[j] = part[0] / (double)n;
+}
+
 __global__ void k_prepare(const double *__restrict__ X, const double *__restrict__ y, int n, int d,
-                          int n_pad, const double *__restrict__ ell_dev, double *__restrict__ xs,
-                          float *__restrict__ xs32, double *__restrict__ ypad) {
+                          int n_pad, const double *__restrict__ ell_dev, const double *__restrict__ center,
+                          double *__restrict__ xs, float *__restrict__ xs32, float *__restrict__ b2,
+                          double *__restrict__ ypad) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pad) return;
   for (int j = 0; j < d; ++j) {
     double v = (i < n) ? X[(size_t)i * d + j] / ell_dev[j] : 0.0;
     xs[(size_t)j * n_pad + i] = v;
   }
+  // fast path: CENTRED scaled inputs in FP32 and their squared norms.  The fast K1 uses
+  // r^2 = |a|^2 + |b|^2 - 2 a.b (one FMA per pair and dimension); centring keeps |a|, |b| small so the
+  // cancellation error stays ~1e-7 like the direct-difference form.
+  float nb = 0.f;
   for (int j = 0; j < 32; ++j) {
-    float v = (i < n && j < d) ? (float)(X[(size_t)i * d + j] / ell_dev[j]) : 0.f;
+    float v = (i < n && j < d) ? (float)((X[(size_t)i * d + j] - center[j]) / ell_dev[j]) : 0.f;
     xs32[(size_t)j * n_pad + i] = v;
+    nb = fmaf(v, v, nb);
   }
+  b2[i] = nb;
   ypad[i] = (i < n) ? y[i] : 0.0;
 }
 
@@ -283,11 +305,15 @@ int ombo_refresh_impl(ombo_ctx *ctx, const ombo_gp_spec *sp, void *state, cudaSt
   double *ell_dev = (double *)(b + lay.off_inv_ell);
   __nv_bfloat16 *bhi = (__nv_bfloat16 *)(b + lay.off_bhi), *blo = (__nv_bfloat16 *)(b + lay.off_blo);
   float *xs32 = (float *)(b + lay.off_xs32), *alpha32 = (float *)(b + lay.off_alpha32);
+  float *b2 = (float *)(b + lay.off_b2);
+  double *center = (double *)(b + lay.off_center);
 
   OMBO_CUDA(cudaMemcpyAsync(ell_dev, sp->ell, sizeof(double) * d, cudaMemcpyHostToDevice, s));
   OMBO_CUDA(cudaMemsetAsync(status, 0, 16, s));
   OMBO_CUDA(cudaMemsetAsync(Linv, 0, (size_t)np * np * 8, s));
-  k_prepare<<<(np + 127) / 128, 128, 0, s>>>(sp->X, sp->y, n, d, np, ell_dev, xs, xs32, alpha /*ypad*/);
+  k_center<<<d, 256, 0, s>>>(sp->X, n, d, center);
+  k_prepare<<<(np + 127) / 128, 128, 0, s>>>(sp->X, sp->y, n, d, np, ell_dev, center, xs, xs32, b2, alpha /*ypad*/);
+  ctx->launches += 1;
   dim3 tb(16, 16), gb(np / 16, np / 16);
   k_build_K<<<gb, tb, 0, s>>>(xs, n, d, np, sp->sigma_f2, sp->sigma_n2 + sp->jitter, sp->kernel, L);
   ctx->launches += 2;

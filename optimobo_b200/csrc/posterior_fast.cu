@@ -33,9 +33,8 @@
 #ifndef NSTB
 #define NSTB 3            // B ring stages (hi+lo = 32 KB each)
 #endif
-#define GEN_WARPS 8        // one generator warp per 8-column (16-byte) operand chunk of the K-block
-#define GEN_THREADS (GEN_WARPS * 32)
-#define FAST_THREADS ((8 + GEN_WARPS) * 32)
+// generator warps GW (template): 8 (one per 16-byte operand chunk of the K-block, R = 4 rows per lane) or
+// 16 (two row halves, R = 2 rows per lane: more warps per scheduler to overlap the FMA / MUFU / ALU phases)
 #define PLANE_BYTES (FM * 128)          // 16 KB
 #define STAGE_BYTES (2 * PLANE_BYTES)   // 32 KB
 
@@ -84,8 +83,11 @@ __device__ __forceinline__ uint32_t elect_one() {
       : "=r"(pred));
   return pred;
 }
+#ifndef MMA_SLEEP_NS
+#define MMA_SLEEP_NS 32    // back-off of the MMA issuer's barrier probes (0 = pure spin; measured equal)
+#endif
 __device__ __forceinline__ void mbar_wait_prof(uint32_t bar, uint32_t parity, unsigned ns, long long &acc, bool on) {
-  if (!on) { mbar_wait_sleep(bar, parity, ns); return; }
+  if (!on) { if (ns) mbar_wait_sleep(bar, parity, ns); else mbar_wait(bar, parity); return; }
   long long t0 = clock64();
   mbar_wait_sleep(bar, parity, ns);
   acc += clock64() - t0;
@@ -208,10 +210,11 @@ extern __shared__ __align__(1024) unsigned char fast_smem[];
 //        issues the MMAs for both tensor cores.  Per MAC this halves the shared-memory operand traffic,
 //        which is what bounds the single-CTA variant (8 KB of operands per 128x128x16 MMA = the full
 //        128 B/clk of the SM's shared memory, before the TMA and K1 writes are even counted).
-template <int DP, int R, bool PAIR>
-__global__ void __launch_bounds__(FAST_THREADS, 1)
+template <int DP, int R, bool PAIR, int GW>
+__global__ void __launch_bounds__((8 + GW) * 32, 1)
 k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                  const FastParams prm) {
+  constexpr int GEN_WARPS = GW, GEN_THREADS = GW * 32;
   constexpr int CW = PAIR ? 256 : 128;           // accumulator chunk width = UMMA N
   constexpr int NSLOT = 512 / CW;                // TMEM accumulator slots
   constexpr int KSH = PAIR ? 2 : 1;              // chunk c needs K-blocks kb < (c + 1) << KSH
@@ -234,9 +237,9 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
   unsigned char *sA = fast_smem + ((1024u - (smem_u32(fast_smem) & 1023u)) & 1023u);   // SWIZZLE_128B: 1024-B aligned
   unsigned char *sB = sA + NSTA * STAGE_BYTES;                 // NSTB x (hi 16 KB, lo 16 KB)
   float *xc = (float *)(sB + NSTB * STAGE_BYTES);              // [DP][128] scaled candidate coords
-  float *xt = xc + (size_t)DP * FM;                            // [2][(DP+1)][64] train slice (+ alpha row)
-  float *mu_sm = xt + 2 * (size_t)(DP + 1) * FK;               // [GEN_WARPS][128]
-  uint64_t *bars = (uint64_t *)(((uintptr_t)(mu_sm + GEN_WARPS * FM) + 15) & ~(uintptr_t)15);
+  float *xt = xc + (size_t)DP * FM;                            // [2][(DP+2)][64] train slice (+ alpha, |b|^2 rows)
+  float *mu_sm = xt + 2 * (size_t)(DP + 2) * FK;               // [8][128]
+  uint64_t *bars = (uint64_t *)(((uintptr_t)(mu_sm + 8 * FM) + 15) & ~(uintptr_t)15);
   uint64_t *a_full = bars, *a_empty = bars + NSTA, *b_full = bars + 2 * NSTA, *b_empty = b_full + NSTB;
   uint64_t *t_full = b_empty + NSTB, *t_empty = t_full + 4;
   uint32_t *tmem_slot = (uint32_t *)(t_empty + 4);
@@ -317,17 +320,17 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
           const int c_first = NSLOT * p, c_last = min(c_first + NSLOT - 1, n_chunks - 1);
           const int kb_end = last_kb(c_last) + 1;
           for (int kb = 0; kb < kb_end; ++kb) {
-            mbar_wait_prof(smem_u32(&a_full[sa]), pa, 32, w_afull, pon);
+            mbar_wait_prof(smem_u32(&a_full[sa]), pa, MMA_SLEEP_NS, w_afull, pon);
             tc_fence_after();
             const uint32_t a_hi = smem_u32(sA + sa * STAGE_BYTES), a_lo = a_hi + PLANE_BYTES;
             for (int c = max(c_first, kb >> KSH); c <= c_last; ++c) {
               const int slot = c & (NSLOT - 1);
               if (kb == 0) {                                  // first touch of this accumulator slot
-                mbar_wait_prof(smem_u32(&t_empty[slot]), ((tph >> slot) & 1) ^ 1, 32, w_tempty, pon);
+                mbar_wait_prof(smem_u32(&t_empty[slot]), ((tph >> slot) & 1) ^ 1, MMA_SLEEP_NS, w_tempty, pon);
                 tph ^= (1u << slot);
                 tc_fence_after();
               }
-              mbar_wait_prof(smem_u32(&b_full[sb]), pb, 32, w_bfull, pon);
+              mbar_wait_prof(smem_u32(&b_full[sb]), pb, MMA_SLEEP_NS, w_bfull, pon);
               tc_fence_after();
               const uint32_t b_hi = smem_u32(sB + sb * STAGE_BYTES), b_lo = b_hi + PLANE_BYTES;
               const uint32_t dcol = tmem_base + (uint32_t)(slot * CW);
@@ -406,83 +409,114 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     // shared-memory reads in the inner loop are two broadcast LDS.128 of (negated) training
     // coordinates per dimension: the LSU traffic that competes with the UMMA operand fetch is
     // 1/R of a row-per-thread mapping.
-    const int gt = tid - 8 * 32;                 // 0..255
-    const int q = gt >> 5;                       // chunk / warp index 0..7
+    const int gt = tid - 8 * 32;                 // 0 .. 32 GW - 1
+    const int q = (gt >> 5) & 7;                 // operand chunk 0..7 of this warp
+    const int rh = gt >> 8;                      // row half (GW = 16 only)
     const bool matern = (prm.gp.kernel == OMBO_KERNEL_MATERN52);
-    constexpr int RB = 4 / R;                    // row batches per K-block
-    constexpr int XT_STRIDE = (DP + 1) * FK;
+    constexpr int RB = 128 / (32 * R * (GW / 8));   // row batches per K-block
+    constexpr int ROW0 = R * RB;                  // rows (in units of 32) owned by one row half
+    constexpr int XT_STRIDE = (DP + 2) * FK;
     uint32_t sa = 0, pa = 0;
     int xbuf = 0;
     long long w_aempty = 0, w_bar = 0; const bool pon = prm.prof != nullptr;
-    // train-slice loader: 16 float4 per row, 16 rows per sweep; rows < DP are NEGATED coords, row DP = alpha
+    // train-slice loader: 16 x 16-byte segments per row, 16 rows per sweep; rows < DP are the centred scaled
+    // coordinates, row DP is sigma_f2 * alpha, row DP + 1 the squared norms |b_i|^2.  cp.async: global -> smem with no register staging, so
+    // the copy of the NEXT slice really is in flight while this K-block is computed.
+    constexpr int LD_ROWS = GEN_THREADS / 16;
     const int ld_j = gt >> 4, ld_o = (gt & 15) * 4;
-    constexpr int LD_SWEEPS = (DP + 1 + 15) / 16;
-    auto load_row = [&](int jj, int kb) -> float4 {
-      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (jj < d) {
-        r = *(const float4 *)(prm.gp.xs32 + (size_t)jj * np + kb * FK + ld_o);
-        r.x = -r.x; r.y = -r.y; r.z = -r.z; r.w = -r.w;
-      } else if (jj == DP) {
-        r = *(const float4 *)(prm.gp.alpha32 + kb * FK + ld_o);
-      }
-      return r;
-    };
+    constexpr int LD_SWEEPS = (DP + 2 + LD_ROWS - 1) / LD_ROWS;
+    auto prefetch_slice = [&](float *dst, int kb) {
 #pragma unroll
-    for (int sw = 0; sw < LD_SWEEPS; ++sw) {
-      const int jj = ld_j + 16 * sw;
-      if (jj <= DP) *(float4 *)(xt + jj * FK + ld_o) = load_row(jj, 0);
-    }
+      for (int sw = 0; sw < LD_SWEEPS; ++sw) {
+        const int jj = ld_j + LD_ROWS * sw;
+        if (jj <= DP + 1) {
+          const float *src = (jj < DP) ? prm.gp.xs32 + (size_t)jj * np + kb * FK + ld_o
+                                       : (jj == DP ? prm.gp.alpha32 : prm.gp.b2_32) + kb * FK + ld_o;
+          const uint32_t sd = smem_u32(dst + jj * FK + ld_o);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(sd), "l"(src) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    prefetch_slice(xt, 0);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     for (long long it = 0; it < n_iter; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
       asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
       for (int e = gt; e < FM * DP; e += GEN_THREADS) {
         const int r_ = e & (FM - 1), j = e >> 7;
         const long long cg = tile * FM + r_;
-        xc[j * FM + r_] = (cg < prm.m && j < d) ? (float)(ombo_pool_coord(prm.pool, cg, j) / prm.gp.ell[j]) : 0.f;
+        // -2 * centred scaled coordinate: r^2 = |a|^2 + |b|^2 + sum_j (-2 a_j) b_j
+        xc[j * FM + r_] = (cg < prm.m && j < d)
+                              ? -2.0f * (float)((ombo_pool_coord(prm.pool, cg, j) - prm.gp.center[j]) / prm.gp.ell[j])
+                              : 0.f;
       }
       asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
       float mu_acc[4] = {0.f, 0.f, 0.f, 0.f};
+      float x[R][DP], a2[R];                       // (-2 x) coordinates and |a|^2 of this lane's rows
+      if (RB == 1) {
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < DP; ++j) { x[rr][j] = xc[j * FM + lane + 32 * (ROW0 * rh + rr)]; acc = fmaf(x[rr][j], x[rr][j], acc); }
+          a2[rr] = 0.25f * acc;
+        }
+      }
       for (int p = 0; p < (mo ? 1 : n_pass); ++p) {
         const int c_last = min(NSLOT * p + NSLOT - 1, n_chunks - 1);
         const int kb_end = mo ? nkb : last_kb(c_last) + 1;
         const bool do_mu = mo || (p == n_pass - 1);
         for (int kb = 0; kb < kb_end; ++kb) {
           const int kb_next = (kb + 1 < kb_end) ? kb + 1 : 0;
-          float4 nxt[LD_SWEEPS];
-#pragma unroll
-          for (int sw = 0; sw < LD_SWEEPS; ++sw) nxt[sw] = load_row(ld_j + 16 * sw, kb_next);   // prefetch
+          prefetch_slice(xt + (xbuf ^ 1) * XT_STRIDE, kb_next);          // lands while this K-block is computed
           const float *xs = xt + xbuf * XT_STRIDE + 8 * q;
           unsigned char *st_hi = sA + sa * STAGE_BYTES, *st_lo = st_hi + PLANE_BYTES;
           if (prm.dbg & 2) mbar_wait_sleep(smem_u32(&a_empty[sa]), pa ^ 1, 32);
 #pragma unroll 1
           for (int rb = 0; rb < ((prm.dbg & 2) ? 0 : RB); ++rb) {
-            float x[R][DP];
+            if (RB > 1) {
 #pragma unroll
-            for (int rr = 0; rr < R; ++rr)
+              for (int rr = 0; rr < R; ++rr) {
+                float acc = 0.f;
 #pragma unroll
-              for (int j = 0; j < DP; ++j) x[rr][j] = xc[j * FM + lane + 32 * (R * rb + rr)];
+                for (int j = 0; j < DP; ++j) {
+                  x[rr][j] = xc[j * FM + lane + 32 * (ROW0 * rh + R * rb + rr)];
+                  acc = fmaf(x[rr][j], x[rr][j], acc);
+                }
+                a2[rr] = 0.25f * acc;
+              }
+            }
             float2 r2[R][4];
+            {
+              const float4 n0 = *(const float4 *)(xs + (DP + 1) * FK);      // |b_i|^2
+              const float4 n1 = *(const float4 *)(xs + (DP + 1) * FK + 4);
 #pragma unroll
-            for (int rr = 0; rr < R; ++rr)
-#pragma unroll
-              for (int e = 0; e < 4; ++e) r2[rr][e] = make_float2(0.f, 0.f);
+              for (int rr = 0; rr < R; ++rr) {
+                const float2 aa = make_float2(a2[rr], a2[rr]);
+                r2[rr][0] = __fadd2_rn(aa, make_float2(n0.x, n0.y));
+                r2[rr][1] = __fadd2_rn(aa, make_float2(n0.z, n0.w));
+                r2[rr][2] = __fadd2_rn(aa, make_float2(n1.x, n1.y));
+                r2[rr][3] = __fadd2_rn(aa, make_float2(n1.z, n1.w));
+              }
+            }
 #pragma unroll
             for (int j = 0; j < DP; ++j) {
               const float4 t0 = *(const float4 *)(xs + j * FK);
               const float4 t1 = *(const float4 *)(xs + j * FK + 4);
 #pragma unroll
               for (int rr = 0; rr < R; ++rr) {
-                const float2 xx = make_float2(x[rr][j], x[rr][j]);
-                const float2 d0 = __fadd2_rn(xx, make_float2(t0.x, t0.y));
-                const float2 d1 = __fadd2_rn(xx, make_float2(t0.z, t0.w));
-                const float2 d2 = __fadd2_rn(xx, make_float2(t1.x, t1.y));
-                const float2 d3 = __fadd2_rn(xx, make_float2(t1.z, t1.w));
-                r2[rr][0] = __ffma2_rn(d0, d0, r2[rr][0]);
-                r2[rr][1] = __ffma2_rn(d1, d1, r2[rr][1]);
-                r2[rr][2] = __ffma2_rn(d2, d2, r2[rr][2]);
-                r2[rr][3] = __ffma2_rn(d3, d3, r2[rr][3]);
+                const float2 xx = make_float2(x[rr][j], x[rr][j]);            // -2 a_j
+                r2[rr][0] = __ffma2_rn(xx, make_float2(t0.x, t0.y), r2[rr][0]);
+                r2[rr][1] = __ffma2_rn(xx, make_float2(t0.z, t0.w), r2[rr][1]);
+                r2[rr][2] = __ffma2_rn(xx, make_float2(t1.x, t1.y), r2[rr][2]);
+                r2[rr][3] = __ffma2_rn(xx, make_float2(t1.z, t1.w), r2[rr][3]);
               }
             }
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { r2[rr][e].x = fmaxf(r2[rr][e].x, 0.f); r2[rr][e].y = fmaxf(r2[rr][e].y, 0.f); }
             const float4 al0 = *(const float4 *)(xs + DP * FK);
             const float4 al1 = *(const float4 *)(xs + DP * FK + 4);
             if (rb == 0 && !mo) mbar_wait_prof(smem_u32(&a_empty[sa]), pa ^ 1, 32, w_aempty, pon);   // stage released by the MMA
@@ -531,7 +565,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                 hi[e] = hb;
                 lo[e] = *reinterpret_cast<uint32_t *>(&l);
               }
-              const int row = lane + 32 * (R * rb + rr);
+              const int row = lane + 32 * (ROW0 * rh + R * rb + rr);
               const uint32_t off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((q ^ (row & 7)) & 7) << 4));
               *(uint4 *)(st_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
               *(uint4 *)(st_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -545,13 +579,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             else mbar_arrive(smem_u32(&a_full[sa]));
           }
           if (++sa == NSTA) { sa = 0; pa ^= 1; }
-          // install the prefetched slice in the other buffer
-          float *xn = xt + (xbuf ^ 1) * XT_STRIDE;
-#pragma unroll
-          for (int sw = 0; sw < LD_SWEEPS; ++sw) {
-            const int jj = ld_j + 16 * sw;
-            if (jj <= DP) *(float4 *)(xn + jj * FK + ld_o) = nxt[sw];
-          }
+          asm volatile("cp.async.wait_group 0;\n" ::: "memory");          // next slice has landed
           { long long t0 = pon ? clock64() : 0;
             asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
             if (pon) w_bar += clock64() - t0; }
@@ -561,14 +589,14 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
       if (pon && lane == 0) { prm.prof[blockIdx.x * 16 + 5 + 0] = w_aempty; if (q == 0) prm.prof[blockIdx.x * 16 + 6] = w_bar; if (q == 7) prm.prof[blockIdx.x * 16 + 7] = w_bar; }
       // mean: one partial sum per (chunk warp, row)
 #pragma unroll
-      for (int r4 = 0; r4 < 4; ++r4) mu_sm[q * FM + lane + 32 * r4] = mu_acc[r4];
+      for (int r4 = 0; r4 < ROW0; ++r4) mu_sm[q * FM + lane + 32 * (ROW0 * rh + r4)] = mu_acc[r4];
       asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
       if (gt < FM) {
         const long long cg = tile * FM + gt;
         if (cg < prm.m) {
           float acc = 0.f;
 #pragma unroll
-          for (int w = 0; w < GEN_WARPS; ++w) acc += mu_sm[w * FM + gt];
+          for (int w = 0; w < 8; ++w) acc += mu_sm[w * FM + gt];
           prm.mu_out[cg] = (double)acc;
           if (mo) prm.var_out[cg] = nan("");
         }
@@ -619,20 +647,20 @@ static int make_b_map(CUtensorMap *map, const void *base, int n_pad, int cs) {
 
 int ombo_fast_path_built() { return 1; }
 
-template <int DP, int R, bool PAIR>
+template <int DP, int R, bool PAIR, int GW>
 static int launch_fast(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensorMap &map_lo, const FastParams &prm,
                        int grid, int cs, cudaStream_t s) {
-  const size_t smem = (size_t)(NSTA + NSTB) * STAGE_BYTES + (size_t)DP * FM * 4 + 2 * (size_t)(DP + 1) * FK * 4 +
-                      GEN_WARPS * FM * 4 + 16 + (2 * NSTA + 2 * NSTB + 8) * 8 + 16 + 1024;
+  const size_t smem = (size_t)(NSTA + NSTB) * STAGE_BYTES + (size_t)DP * FM * 4 + 2 * (size_t)(DP + 2) * FK * 4 +
+                      8 * FM * 4 + 16 + (2 * NSTA + 2 * NSTB + 8) * 8 + 16 + 1024;
   static bool attr = false;
   if (!attr) {
-    OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast<DP, R, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast<DP, R, PAIR, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   ProfScope prof(ctx, s);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(FAST_THREADS);
+  cfg.blockDim = dim3((8 + GW) * 32);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute at[1];
@@ -640,7 +668,7 @@ static int launch_fast(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensorM
   at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  OMBO_CUDA(cudaLaunchKernelEx(&cfg, k_posterior_fast<DP, R, PAIR>, map_hi, map_lo, prm));
+  OMBO_CUDA(cudaLaunchKernelEx(&cfg, k_posterior_fast<DP, R, PAIR, GW>, map_hi, map_lo, prm));
   return OMBO_OK;
 }
 
@@ -678,9 +706,12 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
   grid = (grid + cs - 1) / cs * cs;            // whole clusters; surplus CTAs run a dummy tile
   if (grid > ctx->num_sms) grid = ctx->num_sms / cs * cs;
   const int d = gp.d;
+  bool gw16 = false;
+  { const char *e = getenv("OMBO_FAST_GW"); if (e && atoi(e) == 16) gw16 = true; }
 #define FAST_DISPATCH(DPV, RV)                                                                  \
-  rc = pair ? launch_fast<DPV, RV, true>(ctx, map_hi, map_lo, prm, grid, cs, s)                   \
-            : launch_fast<DPV, RV, false>(ctx, map_hi, map_lo, prm, grid, cs, s)
+  rc = pair ? launch_fast<DPV, RV, true, 8>(ctx, map_hi, map_lo, prm, grid, cs, s)                \
+     : (gw16 && RV == 4) ? launch_fast<DPV, 2, false, 16>(ctx, map_hi, map_lo, prm, grid, cs, s)   \
+                         : launch_fast<DPV, RV, false, 8>(ctx, map_hi, map_lo, prm, grid, cs, s)
   if (d <= 2) { FAST_DISPATCH(2, 4); }
   else if (d <= 4) { FAST_DISPATCH(4, 4); }
   else if (d <= 6) { FAST_DISPATCH(6, 4); }
