@@ -332,8 +332,15 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
               }
               mbar_wait_prof(smem_u32(&b_full[sb]), pb, MMA_SLEEP_NS, w_bfull, pon);
               tc_fence_after();
-              const uint32_t b_hi = smem_u32(sB + sb * STAGE_BYTES), b_lo = b_hi + PLANE_BYTES;
-              const uint32_t dcol = tmem_base + (uint32_t)(slot * CW);
+              uint32_t b_hi = smem_u32(sB + sb * STAGE_BYTES), b_lo = b_hi + PLANE_BYTES;
+              uint32_t dcol = tmem_base + (uint32_t)(slot * CW);
+              uint32_t idesc = IDESC;
+              if (!PAIR && kb == 2 * c + 1) {
+                // second K-block of the diagonal 128x128 block: rows 0..63 of the chunk lie above the
+                // diagonal (zero), so only the lower 64 accumulator columns are touched: N = 64 UMMA
+                b_hi += 64 * 128; b_lo += 64 * 128; dcol += 64;
+                idesc = (IDESC & ~(0x3Fu << 17)) | ((uint32_t)(64 >> 3) << 17);
+              }
               if (!(prm.dbg & 1)) {
 #pragma unroll
                 for (int ks = 0; ks < FK / 16; ++ks) {
@@ -341,13 +348,13 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                   const uint64_t dbh = make_sdesc(b_hi + ks * 32), dbl = make_sdesc(b_lo + ks * 32);
                   const uint32_t acc0 = (kb > 0 || ks > 0) ? 1u : 0u;
                   if (PAIR) {
-                    umma_bf16_2sm(dcol, dah, dbh, IDESC, acc0);
-                    umma_bf16_2sm(dcol, dal, dbh, IDESC, 1u);
-                    umma_bf16_2sm(dcol, dah, dbl, IDESC, 1u);
+                    umma_bf16_2sm(dcol, dah, dbh, idesc, acc0);
+                    umma_bf16_2sm(dcol, dal, dbh, idesc, 1u);
+                    umma_bf16_2sm(dcol, dah, dbl, idesc, 1u);
                   } else {
-                    umma_bf16(dcol, dah, dbh, IDESC, acc0);
-                    umma_bf16(dcol, dal, dbh, IDESC, 1u);
-                    umma_bf16(dcol, dah, dbl, IDESC, 1u);
+                    umma_bf16(dcol, dah, dbh, idesc, acc0);
+                    umma_bf16(dcol, dal, dbh, idesc, 1u);
+                    umma_bf16(dcol, dah, dbl, idesc, 1u);
                   }
                 }
               }
