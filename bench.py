@@ -304,16 +304,33 @@ def main():
         peak = 2 * 4096 ** 3 / (best / 1e3) / 1e12
         peak_src = "cuBLAS DGEMM 4096^3 measured in this run (best of 6)"
     launch_ms = prof_ms / max(1, n_prof)
-    cand_per_launch = m_per_gpu * args.steps * N_OBJ / max(1, n_prof) / N_OBJ * 1.0
-    # one posterior launch covers one GP for one chunk: its algorithmic share is F/G per candidate
-    fl_launch = (fl_cand - 30 * P) / N_OBJ * (m_per_gpu * args.steps * N_OBJ / max(1, n_prof))
+    # one posterior launch covers ONE GP for one chunk of <= 2^20 candidates: its algorithmic share is
+    # (F - A) / G per candidate (the acquisition term A belongs to k_acquire)
+    cand_per_launch = m_per_gpu * args.steps * N_OBJ / max(1, n_prof)
+    fl_launch = (fl_cand - 30 * P) / N_OBJ * cand_per_launch
     achieved = fl_launch / (launch_ms / 1e3) / 1e12 if n_prof else None
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the same size (ncu --set full capture)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[precision]
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": "k_posterior_" + ("fast" if precision == "fast" else "fp64"),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                 "peak_source": peak_src, "launches": n_prof, "avg_launch_ms": launch_ms,
+                "candidates_per_launch": cand_per_launch,
                 "kernel_share_of_step": prof_ms / total_ms if total_ms else None,
                 "flops_per_candidate": fl_cand}
+    if precision == "fast" and achieved:
+        # what the tensor cores actually execute: 3 bf16 products per split-precision MAC, and the 128-wide
+        # diagonal blocks of the triangular factor are multiplied densely (68 of 64 ideal units at n = 1024)
+        nch = N_TRAIN // 128
+        units = sum(2 * c + 2 for c in range(nch)) - 0.5 * nch
+        issued = 3 * units * (128 * 64) * 2              # FLOP per candidate per GP: units of 128 columns x 64 K
+        issued_tflops = issued * cand_per_launch / (launch_ms / 1e3) / 1e12
+        roofline["issued"] = {"tflops": issued_tflops, "frac": issued_tflops / peak,
+                              "note": "bf16x3 split: 3 tensor-core products per algorithmic MAC, "
+                                      "diagonal blocks dense; this is the tensor-pipe work the kernel sustains"}
 
     cpu = None
     if not args.no_cpu_baseline:

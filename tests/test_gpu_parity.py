@@ -403,6 +403,24 @@ def test_posterior_fast_vs_oracle(n, d, m):
         assert torch.equal(mu_b[0].cpu(), torch.as_tensor(mu)) and torch.equal(var_b[0].cpu(), torch.as_tensor(var))
 
 
+def test_posterior_fast_rbf_and_high_dim():
+    if not _cabi.fast_path_available():
+        pytest.skip("fast path not built")
+    for n, d, kernel in ((300, 7, "rbf"), (400, 16, "matern52"), (260, 21, "matern52"), (200, 3, "rbf")):
+        X, Y, ells, sf2 = make_problem(n, d)
+        ell = ells[0] * (2.0 if d > 12 else 1.0)
+        gp = ob.GPModel(X, Y[:, 0], ell, sf2[0], kernel=kernel, device=DEV)
+        st = O.gp_fit_state(X, Y[:, 0], ell, sf2[0], kernel=O.KERNEL_RBF if kernel == "rbf" else O.KERNEL_MATERN52)
+        Xc = np.random.default_rng(d).random((2000, d))
+        mu_o, var_o = O.gp_posterior(st, Xc)
+        mu, var = ob.posterior([gp], Xc, precision="fast")
+        np.testing.assert_allclose(mu[0].cpu().numpy(), mu_o, rtol=1e-3, atol=2e-3 * np.abs(mu_o).max())
+        np.testing.assert_allclose(np.sqrt(var[0].cpu().numpy()), np.sqrt(var_o), rtol=2e-3, atol=2e-3 * np.sqrt(sf2[0]))
+    gp = ob.GPModel(np.random.default_rng(0).random((50, 30)), np.zeros(50), np.ones(30), 1.0, device=DEV)
+    with pytest.raises(_cabi.OmboError, match="d <= 24"):
+        ob.posterior([gp], np.zeros((4, 30)), precision="fast")
+
+
 def test_full_path_fast_ehvi_selection():
     if not _cabi.fast_path_available():
         pytest.skip("fast path not built")
