@@ -115,6 +115,13 @@ int ombo_gp_state_field(int n, int d, int field, size_t *byte_offset, size_t *n_
  * PD status: returns OMBO_ERR_NOT_PD so the host can raise the jitter and retry (GPy jitchol). */
 int ombo_gp_refresh(ombo_ctx *ctx, const ombo_gp_spec *spec, void *state, void *stream);
 
+/* Hyper-parameter fit support: refreshes `state` for the hyper-parameters in `spec`
+ * and returns on the HOST out[0] = negative log marginal likelihood, out[1] = d/d log sigma_f2,
+ * out[2 + j] = d/d log ell_j (d + 2 doubles).  Replaces the O(n^3) work inside GPy's
+ * model.optimize(max_f_eval=1000) (optimisers.py:230 ...); the L-BFGS driver stays on the host.
+ * Synchronises `stream`.  OMBO_ERR_NOT_PD as for ombo_gp_refresh. */
+int ombo_gp_nlml_grad(ombo_ctx *ctx, const ombo_gp_spec *spec, void *state, double *out_host, void *stream);
+
 /* ---- scoring --------------------------------------------------------------- */
 typedef struct {
   int32_t n, d, kernel, reserved;

@@ -24,7 +24,7 @@ SEM_REFERENCE, SEM_EXACT = 0, 1
 
 EXPORTS = [
     "ombo_abi_version", "ombo_has_fast_path", "ombo_last_error", "ombo_ctx_create", "ombo_ctx_destroy", "ombo_n_pad",
-    "ombo_gp_state_bytes", "ombo_gp_state_field", "ombo_gp_refresh", "ombo_score",
+    "ombo_gp_state_bytes", "ombo_gp_state_field", "ombo_gp_refresh", "ombo_gp_nlml_grad", "ombo_score",
     "ombo_score_host", "ombo_acquire_posterior", "ombo_pool_rows", "ombo_launch_count",
     "ombo_pack_key", "ombo_profile_enable", "ombo_profile_read",
 ]
@@ -95,6 +95,7 @@ def lib():
     L.ombo_gp_state_bytes.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_size_t)]
     L.ombo_gp_state_field.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.ombo_gp_refresh.argtypes = [C.c_void_p, C.POINTER(GpSpec), C.c_void_p, C.c_void_p]
+    L.ombo_gp_nlml_grad.argtypes = [C.c_void_p, C.POINTER(GpSpec), C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
     L.ombo_score.argtypes = [C.c_void_p, C.POINTER(Gp), C.c_int, C.POINTER(Pool), C.POINTER(Acq), C.c_int,
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ombo_score_host.argtypes = [C.c_void_p, C.POINTER(Gp), C.c_int, C.POINTER(Pool), C.POINTER(Acq),

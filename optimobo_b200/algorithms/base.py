@@ -19,13 +19,14 @@ import numpy as np
 
 from .. import host_prep
 from ..acquisition import CandidatePool, propose
-from ..fit import fit_hyperparameters
+from ..fit import fit_hyperparameters, fit_hyperparameters_device
 from ..gp import GPModel
 
 
 class PoolOptimiserBase:
     def __init__(self, test_problem, ideal_point=None, max_point=None, n_candidates=1 << 16, precision="auto",
-                 semantics="reference", device="cuda:0", seed=None, hyperparameters=None, max_f_eval=1000):
+                 semantics="reference", device="cuda:0", seed=None, hyperparameters=None, max_f_eval=1000,
+                 fit_on_device=True):
         self.test_problem = test_problem
         self.max_point = max_point
         self.ideal_point = ideal_point
@@ -43,6 +44,7 @@ class PoolOptimiserBase:
         self.rng = np.random.default_rng(seed)
         self.hyperparameters = hyperparameters      # (lengthscale, variance) to skip the fit (parity tests)
         self.max_f_eval = max_f_eval
+        self.fit_on_device = fit_on_device       # likelihood + gradient on the GPU (ombo_gp_nlml_grad)
         self.timings = []
 
     # ---- problem access ------------------------------------------------------------------------
@@ -79,7 +81,9 @@ class PoolOptimiserBase:
         if self.hyperparameters is not None:
             ell, sf2 = self.hyperparameters
         else:
-            ell, sf2 = fit_hyperparameters(X, y, max_f_eval=self.max_f_eval)
+            fit = fit_hyperparameters_device if self.fit_on_device else fit_hyperparameters
+            kw = dict(device=self.device) if self.fit_on_device else {}
+            ell, sf2 = fit(X, y, max_f_eval=self.max_f_eval, **kw)
         t1 = time.perf_counter()
         model = GPModel(X, y, ell, sf2, noise=0.0, device=self.device)
         self._t_fit = getattr(self, "_t_fit", 0.0) + (t1 - t0)

@@ -126,6 +126,17 @@ int ombo_gp_refresh(ombo_ctx *ctx, const ombo_gp_spec *sp, void *state, void *st
   return ombo_refresh_impl(ctx, sp, state, (cudaStream_t)stream);
 }
 
+int ombo_gp_nlml_grad(ombo_ctx *ctx, const ombo_gp_spec *sp, void *state, double *out_host, void *stream) {
+  OMBO_CHECK(ctx && sp && state && out_host, "gp_nlml_grad: NULL argument");
+  OMBO_CHECK(sp->n >= 1 && sp->n <= OMBO_MAX_TRAIN && sp->d >= 1 && sp->d <= OMBO_MAX_DIM, "gp_nlml_grad: n/d out of range");
+  OMBO_CHECK(sp->kernel == OMBO_KERNEL_MATERN52 || sp->kernel == OMBO_KERNEL_RBF, "gp_nlml_grad: unknown kernel");
+  OMBO_CHECK(sp->X && sp->y && sp->ell, "gp_nlml_grad: NULL X/y/ell");
+  OMBO_CHECK(sp->sigma_f2 > 0.0 && sp->sigma_n2 >= 0.0 && sp->jitter >= 0.0, "gp_nlml_grad: bad hyper-parameters");
+  for (int j = 0; j < sp->d; ++j) OMBO_CHECK(sp->ell[j] > 0.0, "gp_nlml_grad: ell[%d] <= 0", j);
+  OMBO_CUDA(cudaSetDevice(ctx->device));
+  return ombo_nlml_grad_impl(ctx, sp, state, out_host, (cudaStream_t)stream);
+}
+
 static int validate_score(ombo_ctx *ctx, const ombo_gp *gps, int n_gp, const ombo_pool *pool, const ombo_acq *acq,
                           int precision) {
   OMBO_CHECK(ctx && gps && pool && acq, "score: NULL argument");

@@ -143,6 +143,7 @@ struct PoolDev {
 
 // ---- internal entry points (one per .cu) ------------------------------------------------
 int ombo_refresh_impl(ombo_ctx *ctx, const ombo_gp_spec *spec, void *state, cudaStream_t s);
+int ombo_nlml_grad_impl(ombo_ctx *ctx, const ombo_gp_spec *spec, void *state, double *out_host, cudaStream_t s);
 int ombo_posterior_fp64(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, long long m,
                         double *mu, double *var, bool want_var, cudaStream_t s);
 int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, long long m,

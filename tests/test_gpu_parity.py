@@ -409,8 +409,12 @@ def test_posterior_fast_rbf_and_high_dim():
     for n, d, kernel in ((300, 7, "rbf"), (400, 16, "matern52"), (260, 21, "matern52"), (200, 3, "rbf")):
         X, Y, ells, sf2 = make_problem(n, d)
         ell = ells[0] * (2.0 if d > 12 else 1.0)
-        gp = ob.GPModel(X, Y[:, 0], ell, sf2[0], kernel=kernel, device=DEV)
-        st = O.gp_fit_state(X, Y[:, 0], ell, sf2[0], kernel=O.KERNEL_RBF if kernel == "rbf" else O.KERNEL_MATERN52)
+        # the RBF Gram matrix is numerically singular without noise (cond > 1e12): that regime belongs to
+        # the FP64 mode; with a 1e-3 noise term it is a fair fast-mode case
+        noise = 1e-3 if kernel == "rbf" else 0.0
+        gp = ob.GPModel(X, Y[:, 0], ell, sf2[0], noise=noise, kernel=kernel, device=DEV)
+        st = O.gp_fit_state(X, Y[:, 0], ell, sf2[0], sigma_n2=noise,
+                            kernel=O.KERNEL_RBF if kernel == "rbf" else O.KERNEL_MATERN52)
         Xc = np.random.default_rng(d).random((2000, d))
         mu_o, var_o = O.gp_posterior(st, Xc)
         mu, var = ob.posterior([gp], Xc, precision="fast")
@@ -441,3 +445,40 @@ def test_full_path_fast_ehvi_selection():
     if a_r[order[0]] - a_r[order[1]] > 5e-3 * a_r[order[0]]:
         assert fast.best_index == ref.best_index
     assert a_r[fast.best_index] >= a_r[order[0]] * (1 - 5e-3)
+
+
+# ------------------------------------------------------------------------------------------
+# section 8f-1: marginal likelihood + gradient on the device (hyper-parameter fit)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,kernel", [(40, 2, "matern52"), (200, 5, "matern52"), (130, 3, "rbf"), (600, 10, "matern52")])
+def test_device_nlml_and_gradient_match_host(n, d, kernel):
+    import ctypes as C
+    from optimobo_b200.fit import _nlml_and_grad
+    from optimobo_b200.gp import _KERNELS, current_stream_ptr
+    rng = np.random.default_rng(n)
+    X = rng.random((n, d)); y = np.sin(3 * X[:, 0]) + X[:, -1] ** 2 + 0.1 * rng.normal(size=n)
+    theta = np.concatenate(([0.3], rng.uniform(-0.4, 0.5, d)))
+    f_host, g_host = _nlml_and_grad(theta, X, y, kernel, 1e-8)
+    dev = torch.device(DEV)
+    Xd, yd = torch.as_tensor(X).to(dev), torch.as_tensor(y).to(dev)
+    state = torch.empty(_cabi.state_bytes(n, d), dtype=torch.uint8, device=dev)
+    ell = (C.c_double * d)(*np.exp(theta[1:]).tolist())
+    spec = _cabi.GpSpec(n=n, d=d, kernel=_KERNELS[kernel], reserved=0, sigma_f2=float(np.exp(theta[0])), sigma_n2=0.0,
+                        jitter=1e-8, X=Xd.data_ptr(), y=yd.data_ptr(), ell=ell)
+    out = (C.c_double * (d + 2))()
+    _cabi.check(_cabi.lib().ombo_gp_nlml_grad(_cabi.Context.get(0).handle, C.byref(spec), C.c_void_p(state.data_ptr()),
+                                              out, current_stream_ptr(dev)))
+    v = np.frombuffer(out, dtype=np.float64, count=d + 2)
+    np.testing.assert_allclose(v[0], f_host, rtol=1e-8, atol=1e-6)
+    np.testing.assert_allclose(v[1:], g_host, rtol=1e-5, atol=1e-6 * np.abs(g_host).max())
+
+
+def test_device_fit_reaches_the_host_optimum():
+    from optimobo_b200.fit import _nlml_and_grad, fit_hyperparameters, fit_hyperparameters_device
+    rng = np.random.default_rng(4)
+    X = rng.random((80, 3)); y = np.cos(4 * X[:, 0]) * X[:, 1] + X[:, 2]
+    ell_d, sf2_d = fit_hyperparameters_device(X, y, device=DEV)
+    ell_h, sf2_h = fit_hyperparameters(X, y)
+    f_d = _nlml_and_grad(np.log(np.concatenate(([sf2_d], ell_d))), X, y, "matern52", 1e-8)[0]
+    f_h = _nlml_and_grad(np.log(np.concatenate(([sf2_h], ell_h))), X, y, "matern52", 1e-8)[0]
+    assert abs(f_d - f_h) <= 1e-3 * abs(f_h) + 1e-3
