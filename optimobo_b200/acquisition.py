@@ -320,13 +320,31 @@ def evaluate(models, spec, X, precision="fp64"):
     return r.acq.cpu().numpy()
 
 
-def propose(models, spec, pool, precision="fp64"):
+def propose(models, spec, pool, precision="fp64", refine_rounds=0, refine_candidates=1 << 14, refine_shrink=0.125):
     """Scores the pool and returns (x_best (d,) ndarray, -acq_best, global_index), mirroring
-    `(res.x, res.fun)` of the reference's `differential_evolution(obj, bounds)` call sites."""
+    `(res.x, res.fun)` of the reference's `differential_evolution(obj, bounds)` call sites.
+
+    refine_rounds > 0 zooms in on the winner the way DE's `polish=True` does
+    after its global phase (optimisers.py:118 defaults): each round scores `refine_candidates` fresh
+    points in a box shrunk by `refine_shrink` around the incumbent (clipped to the pool's box) with
+    the same kernels and keeps the better point; the returned index is -1 once a refined point wins."""
     models = _models_list(models)
     r = score(models, spec, pool, precision=precision)
-    x = pool.rows(r.best_index, 1, device=models[0].device)[0].cpu().numpy()
-    return x, -r.best_value, r.best_index
+    dev = models[0].device
+    x = pool.rows(r.best_index, 1, device=dev)[0].cpu().numpy()
+    best, index = r.best_value, r.best_index
+    if refine_rounds > 0 and pool.lo is not None:
+        lo, hi = pool.lo, pool.hi
+        width = hi - lo
+        for k in range(1, refine_rounds + 1):
+            half = 0.5 * width * (refine_shrink ** k)
+            blo, bhi = np.maximum(lo, x - half), np.minimum(hi, x + half)
+            sub = CandidatePool.counter(refine_candidates, blo, bhi, seed=pool.seed + 7919 * k)
+            rr = score(models, spec, sub, precision=precision)
+            if rr.best_value > best:
+                best, index = rr.best_value, -1
+                x = sub.rows(rr.best_index, 1, device=dev)[0].cpu().numpy()
+    return x, -best, index
 
 
 def propose_host(models, spec, X_host, precision="fp64", index_base=0):

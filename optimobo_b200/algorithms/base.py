@@ -26,7 +26,7 @@ from ..gp import GPModel
 class PoolOptimiserBase:
     def __init__(self, test_problem, ideal_point=None, max_point=None, n_candidates=1 << 16, precision="auto",
                  semantics="reference", device="cuda:0", seed=None, hyperparameters=None, max_f_eval=1000,
-                 fit_on_device=True):
+                 fit_on_device=True, refine_rounds=2):
         self.test_problem = test_problem
         self.max_point = max_point
         self.ideal_point = ideal_point
@@ -45,6 +45,7 @@ class PoolOptimiserBase:
         self.hyperparameters = hyperparameters      # (lengthscale, variance) to skip the fit (parity tests)
         self.max_f_eval = max_f_eval
         self.fit_on_device = fit_on_device       # likelihood + gradient on the GPU (ombo_gp_nlml_grad)
+        self.refine_rounds = refine_rounds       # zoom rounds around the pool winner (DE's polish step)
         self.timings = []
 
     # ---- problem access ------------------------------------------------------------------------
@@ -105,7 +106,8 @@ class PoolOptimiserBase:
         t0 = time.perf_counter()
         pool = CandidatePool.counter(self.n_candidates, self.test_problem.xl, self.test_problem.xu,
                                      seed=int(self.rng.integers(1, 2 ** 62)))
-        x, neg_value, index = propose(models, spec, pool, precision=self._precision_for(models))
+        x, neg_value, index = propose(models, spec, pool, precision=self._precision_for(models),
+                                      refine_rounds=self.refine_rounds)
         self.timings.append(dict(fit_s=getattr(self, "_t_fit", 0.0), refresh_s=getattr(self, "_t_refresh", 0.0),
                                  score_s=time.perf_counter() - t0, n_candidates=self.n_candidates))
         self._t_fit = self._t_refresh = 0.0

@@ -82,50 +82,58 @@ __global__ void k_build_K(const double *__restrict__ xs, int n, int d, int n_pad
 }
 
 // ------------------------------------------------------------------------------------------
-// diagonal block: unblocked Cholesky in smem + inverse of the 64x64 triangular factor
-__global__ void __launch_bounds__(256) k_potrf_diag(double *__restrict__ A, int ld, int kb, int n,
-                                                    double *__restrict__ dinv, int *__restrict__ status) {
-  extern __shared__ __align__(16) double dyn_smem[];
-  double (*a)[LDS] = (double (*)[LDS])dyn_smem;
-  double (*inv)[LDS] = (double (*)[LDS])(dyn_smem + NB * LDS);
-  const int tid = threadIdx.x;
+// diagonal block: Cholesky of a 64x64 block + inverse of its triangular factor, 64 threads.
+// Thread t keeps ROW t of the block in registers (fully unrolled, compile-time register indices); per
+// elimination step only the current column travels through shared memory (two barriers of two warps),
+// so the 64 dependent steps cost ~100 cycles each instead of three 256-thread barriers + smem sweeps.
+__global__ void __launch_bounds__(64) k_potrf_diag(double *__restrict__ A, int ld, int kb, int n,
+                                                   double *__restrict__ dinv, int *__restrict__ status) {
+  __shared__ double Ls[NB][NB + 1];
+  __shared__ double col[NB];
+  __shared__ double pivot;
+  const int t = threadIdx.x;
   double *blk = A + ((size_t)kb * NB) * ld + (size_t)kb * NB;
-  for (int e = tid; e < NB * NB; e += 256) a[e / NB][e % NB] = blk[(size_t)(e / NB) * ld + (e % NB)];
-  __syncthreads();
+  double a[NB];
+#pragma unroll
+  for (int k = 0; k < NB; ++k) a[k] = blk[(size_t)t * ld + k];
+#pragma unroll
   for (int j = 0; j < NB; ++j) {
-    if (tid == 0) {
-      double p = a[j][j];
-      if (!(p > 0.0)) {
-        atomicCAS(status, 0, kb * NB + j + 1);
-        p = 1.0;
-      }
-      a[j][j] = sqrt(p);
+    if (t == j) {
+      double p = a[j];
+      if (!(p > 0.0)) { atomicCAS(status, 0, kb * NB + j + 1); p = 1.0; }
+      pivot = sqrt(p);
     }
     __syncthreads();
-    if (tid > j && tid < NB) a[tid][j] /= a[j][j];
+    const double piv = pivot;
+    if (t == j) a[j] = piv;
+    if (t > j) a[j] = a[j] / piv;
+    col[t] = a[j];                 // column j of L (entries t < j are never read)
     __syncthreads();
-    // trailing update of the lower triangle: a[i][k] -= a[i][j] * a[k][j], j < k <= i
-    for (int e = tid; e < NB * NB; e += 256) {
-      int i = e / NB, k = e % NB;
-      if (k > j && i >= k) a[i][k] -= a[i][j] * a[k][j];
+    if (t > j) {
+#pragma unroll
+      for (int k = j + 1; k < NB; ++k)
+        if (k <= t) a[k] -= a[j] * col[k];
     }
-    __syncthreads();
   }
-  // inverse: thread c solves L x = e_c
-  if (tid < NB) {
-    const int c = tid;
-    for (int i = 0; i < NB; ++i) {
-      double s = (i == c) ? 1.0 : 0.0;
-      for (int k = 0; k < i; ++k) s -= a[i][k] * ((k >= c) ? inv[k][c] : 0.0);
-      inv[i][c] = (i >= c) ? s / a[i][i] : 0.0;
-    }
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    const double v = (k <= t) ? a[k] : 0.0;
+    Ls[t][k] = v;
+    blk[(size_t)t * ld + k] = v;
   }
   __syncthreads();
-  for (int e = tid; e < NB * NB; e += 256) {
-    int i = e / NB, k = e % NB;
-    blk[(size_t)i * ld + k] = (k <= i) ? a[i][k] : 0.0;
-    dinv[(size_t)kb * NB * NB + e] = inv[i][k];
+  // inverse: thread t owns COLUMN t of X = L^-1 in registers; L is read from smem by broadcast
+  double x[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    double sacc = (i == t) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < i; ++k)
+      if (k >= t) sacc -= Ls[i][k] * x[k];
+    x[i] = (i >= t) ? sacc / Ls[i][i] : 0.0;
   }
+#pragma unroll
+  for (int i = 0; i < NB; ++i) dinv[(size_t)kb * NB * NB + (size_t)i * NB + t] = x[i];
 }
 
 // C(64x64) (+)= sign * As(64x64) * Bs(64x64)^T with both operands k-contiguous in smem
@@ -320,13 +328,12 @@ int ombo_refresh_impl(ombo_ctx *ctx, const ombo_gp_spec *sp, void *state, cudaSt
   const size_t sm2 = (size_t)2 * NB * LDS * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
-    OMBO_CUDA(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
     OMBO_CUDA(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
     OMBO_CUDA(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
     attr_set = true;
   }
   for (int kb = 0; kb < nb; ++kb) {
-    k_potrf_diag<<<1, 256, sm2, s>>>(L, np, kb, n, dinv, status);
+    k_potrf_diag<<<1, 64, 0, s>>>(L, np, kb, n, dinv, status);
     ctx->launches += 1;
     int rem = nb - kb - 1;
     if (rem > 0) {

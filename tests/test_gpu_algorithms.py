@@ -135,6 +135,30 @@ def test_score_sharded_single_process_matches_score():
     assert unpack_key(max(keys))[1] == ref.best_index
 
 
+def test_refinement_never_worse_and_usually_better():
+    rng = np.random.default_rng(1)
+    X = rng.random((200, 6)); y = ((X - 0.37) ** 2).sum(1)
+    gp = ob.GPModel(X, y, 0.8 * np.ones(6), 1.0, device="cuda:0")
+    pool = ob.CandidatePool.counter(1 << 14, np.zeros(6), np.ones(6), seed=2)
+    spec = ob.spec_ei(y.min(), 0.0)
+    x0, f0, i0 = ob.propose([gp], spec, pool)
+    x1, f1, i1 = ob.propose([gp], spec, pool, refine_rounds=3)
+    assert f1 <= f0 and np.all(x1 >= 0) and np.all(x1 <= 1)
+    assert (i1 == i0 and np.array_equal(x0, x1)) or (i1 == -1 and f1 < f0)
+    np.testing.assert_allclose(ob.expected_improvement(x1, gp, y.min())[0], -f1, rtol=1e-9)
+
+
+def test_every_acquisition_kind_in_both_precisions():
+    import runpy, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cwd = os.getcwd()
+    os.chdir(root)
+    try:
+        runpy.run_path(os.path.join(root, "scripts", "sanitize_small.py"), run_name="__main__")
+    finally:
+        os.chdir(cwd)
+
+
 def test_nccl_two_ranks_agree_with_single_gpu():
     import os
     import subprocess
