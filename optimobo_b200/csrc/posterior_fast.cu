@@ -27,12 +27,6 @@
 #define FM 128            // candidates per tile (UMMA M)
 #define FN 128            // columns per accumulator chunk (UMMA N)
 #define FK 64             // K-block: 64 bf16 = 128 B = one swizzle atom row
-#ifndef NSTA
-#define NSTA 3            // A ring stages (hi+lo = 32 KB each)
-#endif
-#ifndef NSTB
-#define NSTB 3            // B ring stages (hi+lo = 32 KB each)
-#endif
 // generator warps GW (template): 8 (one per 16-byte operand chunk of the K-block, R = 4 rows per lane) or
 // 16 (two row halves, R = 2 rows per lane: more warps per scheduler to overlap the FMA / MUFU / ALU phases)
 #define PLANE_BYTES (FM * 128)          // 16 KB
@@ -227,14 +221,21 @@ extern __shared__ __align__(1024) unsigned char fast_smem[];
 //        issues the MMAs for both tensor cores.  Per MAC this halves the shared-memory operand traffic,
 //        which is what bounds the single-CTA variant (8 KB of operands per 128x128x16 MMA = the full
 //        128 B/clk of the SM's shared memory, before the TMA and K1 writes are even counted).
-template <int DP, int R, bool PAIR, int GW>
+// MODE = 0: single CTA, 128-column chunks (UMMA N = 128, 96.8 cycles each in SS mode)
+//        1: cta_group::2 pair (see above)
+//        2: single CTA, 256-column chunks (UMMA N = 256 at 160.8 cycles = 17 % fewer cycles per MAC; the
+//           diagonal K-blocks shrink N to 192 / 128 / 64), B ring entries are single planes so the lo
+//           plane of a unit can still be in flight while its hi plane is being multiplied
+template <int DP, int R, int MODE, int GW>
 __global__ void __launch_bounds__((8 + GW) * 32, 1)
 k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                  const FastParams prm) {
+  constexpr bool PAIR = (MODE == 1), WIDE = (MODE == 2);
+  constexpr int NSTA = WIDE ? 2 : 3, NSTB = WIDE ? 4 : 3;     // ring depths (32 KB entries, 192 KB in all modes)
   constexpr int GEN_WARPS = GW, GEN_THREADS = GW * 32;
-  constexpr int CW = PAIR ? 256 : 128;           // accumulator chunk width = UMMA N
+  constexpr int CW = (PAIR || WIDE) ? 256 : 128; // accumulator chunk width = widest UMMA N
   constexpr int NSLOT = 512 / CW;                // TMEM accumulator slots
-  constexpr int KSH = PAIR ? 2 : 1;              // chunk c needs K-blocks kb < (c + 1) << KSH
+  constexpr int KSH = (PAIR || WIDE) ? 2 : 1;    // chunk c needs K-blocks kb < (c + 1) << KSH
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CW >> 3) << 17) |
                              ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -300,6 +301,17 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
           const int kb_end = last_kb(c_last) + 1;
           for (int kb = 0; kb < kb_end; ++kb) {
             for (int c = max(c_first, kb >> KSH); c <= c_last; ++c) {
+              if (WIDE) {                    // two ring entries per unit: the hi plane, then the lo plane
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl) {
+                  mbar_wait_prof(smem_u32(&b_empty[st]), ph ^ 1, 64, w_bempty, pon);
+                  const uint32_t full = smem_u32(&b_full[st]);
+                  mbar_expect_tx(full, STAGE_BYTES);
+                  tma_load_2d(smem_u32(sB + st * STAGE_BYTES), pl == 0 ? &map_hi : &map_lo, full, kb * FK, c * CW);
+                  if (++st == NSTB) { st = 0; ph ^= 1; }
+                }
+                continue;
+              }
               mbar_wait_prof(smem_u32(&b_empty[st]), ph ^ 1, 64, w_bempty, pon);
               const uint32_t dst = smem_u32(sB + st * STAGE_BYTES);
               if (PAIR) {                    // this CTA's half of the 256-row B tile; bytes counted on the leader
@@ -346,6 +358,39 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                 mbar_wait_prof(smem_u32(&t_empty[slot]), ((tph >> slot) & 1) ^ 1, MMA_SLEEP_NS, w_tempty, pon);
                 tph ^= (1u << slot);
                 tc_fence_after();
+              }
+              if (WIDE) {
+                // rows of the chunk above the diagonal band are zero: skip them (N = 256, 192, 128 or 64)
+                const int r0 = max(0, kb - 4 * c) * 64;
+                const uint32_t dcolw = tmem_base + (uint32_t)(slot * CW + r0);
+                const uint32_t idw = (IDESC & ~(0x3Fu << 17)) | ((uint32_t)((CW - r0) >> 3) << 17);
+                // hi plane: A_hi.B_hi and A_lo.B_hi
+                mbar_wait_prof(smem_u32(&b_full[sb]), pb, MMA_SLEEP_NS, w_bfull, pon);
+                tc_fence_after();
+                uint32_t bp = smem_u32(sB + sb * STAGE_BYTES) + (uint32_t)(r0 * 128);
+                if (!(prm.dbg & 1)) {
+#pragma unroll
+                  for (int ks = 0; ks < FK / 16; ++ks) {
+                    const uint64_t dbh = make_sdesc(bp + ks * 32);
+                    umma_bf16(dcolw, make_sdesc(a_hi + ks * 32), dbh, idw, (kb > 0 || ks > 0) ? 1u : 0u);
+                    umma_bf16(dcolw, make_sdesc(a_lo + ks * 32), dbh, idw, 1u);
+                  }
+                }
+                umma_commit(smem_u32(&b_empty[sb]));
+                if (++sb == NSTB) { sb = 0; pb ^= 1; }
+                // lo plane: A_hi.B_lo
+                mbar_wait_prof(smem_u32(&b_full[sb]), pb, MMA_SLEEP_NS, w_bfull, pon);
+                tc_fence_after();
+                bp = smem_u32(sB + sb * STAGE_BYTES) + (uint32_t)(r0 * 128);
+                if (!(prm.dbg & 1)) {
+#pragma unroll
+                  for (int ks = 0; ks < FK / 16; ++ks)
+                    umma_bf16(dcolw, make_sdesc(a_hi + ks * 32), make_sdesc(bp + ks * 32), idw, 1u);
+                }
+                umma_commit(smem_u32(&b_empty[sb]));
+                if (++sb == NSTB) { sb = 0; pb ^= 1; }
+                if (kb == last_kb(c)) umma_commit(smem_u32(&t_full[slot]));      // chunk complete
+                continue;
               }
               mbar_wait_prof(smem_u32(&b_full[sb]), pb, MMA_SLEEP_NS, w_bfull, pon);
               tc_fence_after();
@@ -657,12 +702,12 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int make_b_map(CUtensorMap *map, const void *base, int n_pad, int cs) {
+static int make_b_map(CUtensorMap *map, const void *base, int n_pad, int box_rows) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { ombo_set_error("cuTensorMapEncodeTiled is not available from the driver"); return OMBO_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)n_pad, (cuuint64_t)n_pad};
   cuuint64_t strides[1] = {(cuuint64_t)n_pad * 2};
-  cuuint32_t box[2] = {FK, (cuuint32_t)(FN / cs)};
+  cuuint32_t box[2] = {FK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -673,14 +718,14 @@ static int make_b_map(CUtensorMap *map, const void *base, int n_pad, int cs) {
 
 int ombo_fast_path_built() { return 1; }
 
-template <int DP, int R, bool PAIR, int GW>
+template <int DP, int R, int MODE, int GW>
 static int launch_fast(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensorMap &map_lo, const FastParams &prm,
                        int grid, int cs, cudaStream_t s) {
-  const size_t smem = (size_t)(NSTA + NSTB) * STAGE_BYTES + (size_t)DP * FM * 4 + 2 * (size_t)(DP + 2) * FK * 4 +
-                      8 * FM * 4 + 16 + (2 * NSTA + 2 * NSTB + 8) * 8 + 16 + 1024;
+  const size_t smem = (size_t)6 * STAGE_BYTES + (size_t)DP * FM * 4 + 2 * (size_t)(DP + 2) * FK * 4 +
+                      8 * FM * 4 + 16 + (2 * 3 + 2 * 4 + 8) * 8 + 16 + 1024;
   static bool attr = false;
   if (!attr) {
-    OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast<DP, R, PAIR, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast<DP, R, MODE, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   ProfScope prof(ctx, s);
@@ -694,7 +739,7 @@ static int launch_fast(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensorM
   at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  OMBO_CUDA(cudaLaunchKernelEx(&cfg, k_posterior_fast<DP, R, PAIR, GW>, map_hi, map_lo, prm));
+  OMBO_CUDA(cudaLaunchKernelEx(&cfg, k_posterior_fast<DP, R, MODE, GW>, map_hi, map_lo, prm));
   return OMBO_OK;
 }
 
@@ -705,20 +750,20 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
     ombo_set_error("fast precision mode supports d <= 24 (got %d); use OMBO_PREC_FP64", gp.d);
     return OMBO_ERR_UNSUPPORTED;
   }
-  // default: single-CTA UMMA (M = 128, N = 128): measured faster end to end (round 1: 1.5e8 vs 1.3e8
-  // cand/s) because the pair variant couples two CTAs' K1 generators to one MMA stream.
-  // OMBO_FAST_MODE=2 selects the cta_group::2 pair variant, OMBO_FAST_CLUSTER the multicast cluster
-  // size of the single-CTA variant (both for experiments).
+  // default: single-CTA UMMA with 256-column chunks (MODE 2).  Experiments: OMBO_FAST_MODE=1 selects the
+  // 128-column variant (OMBO_FAST_CLUSTER its multicast cluster size), OMBO_FAST_MODE=2 the cta_group::2
+  // pair variant (slower end to end: it couples two CTAs' K1 generators to one MMA stream).
   long long tiles = (m + FM - 1) / FM;
-  bool pair = false;
+  bool pair = false, wide = true;
   int cs = 1;
-  { const char *e = getenv("OMBO_FAST_MODE"); if (e && atoi(e) == 2) pair = true; }
-  if (!pair) { const char *e = getenv("OMBO_FAST_CLUSTER"); if (e) cs = atoi(e); if (cs != 1 && cs != 2 && cs != 4) cs = 1; if (tiles < cs) cs = 1; }
+  { const char *e = getenv("OMBO_FAST_MODE"); if (e) { pair = atoi(e) == 2; wide = atoi(e) == 3; } }
+  if (!pair && !wide) { const char *e = getenv("OMBO_FAST_CLUSTER"); if (e) cs = atoi(e); if (cs != 1 && cs != 2 && cs != 4) cs = 1; if (tiles < cs) cs = 1; }
   if (pair) cs = 2;
   CUtensorMap map_hi, map_lo;
-  int rc = make_b_map(&map_hi, gp.bhi, gp.n_pad, pair ? 1 : cs);
+  const int box_rows = wide ? 256 : (pair ? 128 : 128 / cs);
+  int rc = make_b_map(&map_hi, gp.bhi, gp.n_pad, box_rows);
   if (rc) return rc;
-  rc = make_b_map(&map_lo, gp.blo, gp.n_pad, pair ? 1 : cs);
+  rc = make_b_map(&map_lo, gp.blo, gp.n_pad, box_rows);
   if (rc) return rc;
   FastParams prm;
   prm.gp = gp; prm.pool = pool; prm.m = m; prm.mu_out = mu; prm.var_out = var; prm.mean_only = want_var ? 0 : 1;
@@ -735,9 +780,10 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
   bool gw16 = false;
   { const char *e = getenv("OMBO_FAST_GW"); if (e && atoi(e) == 16) gw16 = true; }
 #define FAST_DISPATCH(DPV, RV)                                                                  \
-  rc = pair ? launch_fast<DPV, RV, true, 8>(ctx, map_hi, map_lo, prm, grid, cs, s)                \
-     : (gw16 && RV == 4) ? launch_fast<DPV, 2, false, 16>(ctx, map_hi, map_lo, prm, grid, cs, s)   \
-                         : launch_fast<DPV, RV, false, 8>(ctx, map_hi, map_lo, prm, grid, cs, s)
+  rc = pair ? launch_fast<DPV, RV, 1, 8>(ctx, map_hi, map_lo, prm, grid, cs, s)                   \
+     : wide ? launch_fast<DPV, RV, 2, 8>(ctx, map_hi, map_lo, prm, grid, cs, s)                   \
+     : (gw16 && RV == 4) ? launch_fast<DPV, 2, 0, 16>(ctx, map_hi, map_lo, prm, grid, cs, s)       \
+                         : launch_fast<DPV, RV, 0, 8>(ctx, map_hi, map_lo, prm, grid, cs, s)
   if (d <= 2) { FAST_DISPATCH(2, 4); }
   else if (d <= 4) { FAST_DISPATCH(4, 4); }
   else if (d <= 6) { FAST_DISPATCH(6, 4); }
