@@ -41,6 +41,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -116,6 +119,17 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_size() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// linear bulk copies (TMA without a tensor map): smem -> global with bulk-group completion,
+// global -> smem with mbarrier transaction completion
+__device__ __forceinline__ void bulk_store(void *gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t sdst, const void *gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(sdst),
+               "l"(gsrc), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t local, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local), "r"(rank));
@@ -207,6 +221,7 @@ struct FastParams {
   PoolDev pool;
   long long m;
   double *mu_out, *var_out;
+  unsigned char *kcache;   // per-CTA cache of generated K* blocks (n_pad/64 x 32 KB), L2 resident
   long long *prof;   // optional per-CTA wait-cycle counters (timing experiments)
   int mean_only;     // 1: this GP's variance is not read by the acquisition -> K1 + mean only, no MMA
   int dbg;   // bit 0: skip the MMAs, bit 1: skip the K1 math (timing experiments only; results are garbage)
@@ -231,7 +246,10 @@ __global__ void __launch_bounds__((8 + GW) * 32, 1)
 k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                  const FastParams prm) {
   constexpr bool PAIR = (MODE == 1), WIDE = (MODE == 2);
-  constexpr int NSTA = WIDE ? 2 : 3, NSTB = WIDE ? 4 : 3;     // ring depths (32 KB entries, 192 KB in all modes)
+#ifndef WIDE_NSTA
+#define WIDE_NSTA 2
+#endif
+  constexpr int NSTA = WIDE ? WIDE_NSTA : 3, NSTB = 6 - NSTA;  // ring depths (32 KB entries, 192 KB in all modes)
   constexpr int GEN_WARPS = GW, GEN_THREADS = GW * 32;
   constexpr int CW = (PAIR || WIDE) ? 256 : 128; // accumulator chunk width = widest UMMA N
   constexpr int NSLOT = 512 / CW;                // TMEM accumulator slots
@@ -537,10 +555,34 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
       for (int p = 0; p < (mo ? 1 : n_pass); ++p) {
         const int c_last = min(NSLOT * p + NSLOT - 1, n_chunks - 1);
         const int kb_end = mo ? nkb : last_kb(c_last) + 1;
-        const bool do_mu = mo || (p == n_pass - 1);
+        // K* blocks generated by an earlier pass of this tile are not recomputed: they were copied to a
+        // per-CTA cache in L2 (bulk store of the 32 KB operand stage) and are streamed back by a bulk load
+        // that completes the stage's full barrier.  Every K* block is generated exactly once per tile.
+        const bool use_cache = !PAIR && !mo && prm.kcache != nullptr;
+        const int kb_cached = (use_cache && p > 0 && !(prm.dbg & 16)) ? last_kb(min(NSLOT * (p - 1) + NSLOT - 1, n_chunks - 1)) + 1 : 0;
+        const bool store_cache = use_cache && (p + 1 < n_pass);
+        unsigned char *kc = prm.kcache + (size_t)blockIdx.x * nkb * STAGE_BYTES;
+        if (kb_cached > 0 && gt == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // stores landed
         for (int kb = 0; kb < kb_end; ++kb) {
+          const bool do_mu = mo || !use_cache ? (mo || p == n_pass - 1) : true;
           const int kb_next = (kb + 1 < kb_end) ? kb + 1 : 0;
           prefetch_slice(xt + (xbuf ^ 1) * XT_STRIDE, kb_next);          // lands while this K-block is computed
+          if (kb < kb_cached) {
+            if (gt == 0) {
+              // ONE thread performs all GEN_WARPS arrivals of this phase, and only after the stage has been
+              // released: the other warps do not wait on a_empty here, so an arrival of their own could land
+              // in the still-open phase of two K-blocks ago (its bulk load may not have completed yet)
+              mbar_wait_prof(smem_u32(&a_empty[sa]), pa ^ 1, 32, w_aempty, pon);
+              mbar_expect_tx(smem_u32(&a_full[sa]), STAGE_BYTES);
+              mbar_arrive_n(smem_u32(&a_full[sa]), GEN_WARPS - 1);
+              bulk_load(smem_u32(sA + sa * STAGE_BYTES), kc + (size_t)kb * STAGE_BYTES, STAGE_BYTES, smem_u32(&a_full[sa]));
+            }
+            if (++sa == NSTA) { sa = 0; pa ^= 1; }
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
+            xbuf ^= 1;
+            continue;
+          }
           const float *xs = xt + xbuf * XT_STRIDE + 8 * q;
           unsigned char *st_hi = sA + sa * STAGE_BYTES, *st_lo = st_hi + PLANE_BYTES;
           if (prm.dbg & 2) mbar_wait_sleep(smem_u32(&a_empty[sa]), pa ^ 1, 32);
@@ -649,11 +691,15 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             if (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&a_full[sa]), 0));   // the leader's MMA consumes both halves
             else mbar_arrive(smem_u32(&a_full[sa]));
           }
+          const uint32_t stage_just_written = smem_u32(sA + sa * STAGE_BYTES);
           if (++sa == NSTA) { sa = 0; pa ^= 1; }
           asm volatile("cp.async.wait_group 0;\n" ::: "memory");          // next slice has landed
+          // the previous cache store must have finished READING its stage before anyone overwrites it
+          if (store_cache && gt == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
           { long long t0 = pon ? clock64() : 0;
             asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
             if (pon) w_bar += clock64() - t0; }
+          if (store_cache && gt == 0 && !(prm.dbg & 8)) bulk_store(kc + (size_t)kb * STAGE_BYTES, stage_just_written, STAGE_BYTES);
           xbuf ^= 1;
         }
       }
@@ -776,6 +822,13 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
   int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
   grid = (grid + cs - 1) / cs * cs;            // whole clusters; surplus CTAs run a dummy tile
   if (grid > ctx->num_sms) grid = ctx->num_sms / cs * cs;
+  prm.kcache = nullptr;
+  if (!pair && want_var && gp.n_pad > (wide ? 512 : 512) && !getenv("OMBO_FAST_NOCACHE")) {   // more than one TMEM pass
+    rc = ombo_ws_reserve(&ctx->ws_scratch, &ctx->ws_scratch_bytes, (size_t)grid * (gp.n_pad / FK) * STAGE_BYTES);
+    if (rc) return rc;
+    prm.kcache = (unsigned char *)ctx->ws_scratch;
+    if (getenv("OMBO_FAST_ZEROCACHE")) OMBO_CUDA(cudaMemsetAsync(prm.kcache, 0, (size_t)grid * (gp.n_pad / FK) * STAGE_BYTES, s));
+  }
   const int d = gp.d;
   bool gw16 = false;
   { const char *e = getenv("OMBO_FAST_GW"); if (e && atoi(e) == 16) gw16 = true; }
