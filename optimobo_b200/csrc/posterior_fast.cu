@@ -247,7 +247,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                  const FastParams prm) {
   constexpr bool PAIR = (MODE == 1), WIDE = (MODE == 2);
 #ifndef WIDE_NSTA
-#define WIDE_NSTA 2
+#define WIDE_NSTA 3
 #endif
   constexpr int NSTA = WIDE ? WIDE_NSTA : 3, NSTB = 6 - NSTA;  // ring depths (32 KB entries, 192 KB in all modes)
   constexpr int GEN_WARPS = GW, GEN_THREADS = GW * 32;
