@@ -834,6 +834,7 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
   { const char *e = getenv("OMBO_FAST_GW"); if (e && atoi(e) == 16) gw16 = true; }
 #define FAST_DISPATCH(DPV, RV)                                                                  \
   rc = pair ? launch_fast<DPV, RV, 1, 8>(ctx, map_hi, map_lo, prm, grid, cs, s)                   \
+     : (wide && gw16 && RV == 4) ? launch_fast<DPV, 2, 2, 16>(ctx, map_hi, map_lo, prm, grid, cs, s) \
      : wide ? launch_fast<DPV, RV, 2, 8>(ctx, map_hi, map_lo, prm, grid, cs, s)                   \
      : (gw16 && RV == 4) ? launch_fast<DPV, 2, 0, 16>(ctx, map_hi, map_lo, prm, grid, cs, s)       \
                          : launch_fast<DPV, RV, 0, 8>(ctx, map_hi, map_lo, prm, grid, cs, s)

@@ -64,6 +64,17 @@ def score_sharded(models, spec, pool: CandidatePool, precision="fp64", group=Non
     if world == 1:
         host = res.best_dev.cpu()
         return float(host[:1].view(torch.float64)[0]), int(host[1])
+    if pool.index_base + pool.m > _MASK32:
+        # the packed key carries 32 index bits: pools beyond 2^32 candidates fall back to an exact
+        # all-gather of the 16-byte (value, index) pairs (still one collective)
+        pairs = [torch.empty_like(res.best_dev) for _ in range(world)]
+        dist.all_gather(pairs, res.best_dev, group=group)
+        host = torch.stack(pairs).cpu()
+        vals = host[:, 0].contiguous().view(torch.float64).numpy()
+        idxs = host[:, 1].numpy()
+        vals = np.where(np.isnan(vals), -np.inf, vals)
+        order = np.lexsort((idxs, -vals))
+        return float(vals[order[0]]), int(idxs[order[0]])
     key = torch.empty((1,), dtype=torch.int64, device=dev)
     ctx = _cabi.Context.get(dev.index)
     with torch.cuda.device(dev):
