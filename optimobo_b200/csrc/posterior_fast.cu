@@ -139,6 +139,9 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t local, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_n_cluster(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -244,7 +247,7 @@ extern __shared__ __align__(1024) unsigned char fast_smem[];
 template <int DP, int R, int MODE, int GW>
 __global__ void __launch_bounds__((8 + GW) * 32, 1)
 k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-                 const FastParams prm) {
+                 const __grid_constant__ CUtensorMap map_kc, const FastParams prm) {
   constexpr bool PAIR = (MODE == 1), WIDE = (MODE == 2);
 #ifndef WIDE_NSTA
 #define WIDE_NSTA 3
@@ -286,7 +289,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
       mbar_init(smem_u32(&a_empty[s]), 1);
     }
     for (int s = 0; s < NSTB; ++s) {
-      mbar_init(smem_u32(&b_full[s]), PAIR ? 2 : 1);
+      mbar_init(smem_u32(&b_full[s]), 1);
       mbar_init(smem_u32(&b_empty[s]), PAIR ? 1 : cs);
     }
     for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&t_full[s]), 1); mbar_init(smem_u32(&t_empty[s]), PAIR ? 8 : 4); }
@@ -333,8 +336,10 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
               mbar_wait_prof(smem_u32(&b_empty[st]), ph ^ 1, 64, w_bempty, pon);
               const uint32_t dst = smem_u32(sB + st * STAGE_BYTES);
               if (PAIR) {                    // this CTA's half of the 256-row B tile; bytes counted on the leader
+                // the leader alone arms its barrier, with the bytes of BOTH halves (a remote expect_tx with
+                // release.cluster semantics costs the peer's producer ~1 us per stage and throttles the ring)
                 const uint32_t full = mapa_rank(smem_u32(&b_full[st]), 0);
-                mbar_expect_tx_cluster(full, STAGE_BYTES);
+                if (crank == 0) mbar_expect_tx(smem_u32(&b_full[st]), 2 * STAGE_BYTES);
                 tma_load_2d_2sm(dst, &map_hi, full, kb * FK, c * CW + (int)crank * 128);
                 tma_load_2d_2sm(dst + PLANE_BYTES, &map_lo, full, kb * FK, c * CW + (int)crank * 128);
               } else {
@@ -558,7 +563,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
         // K* blocks generated by an earlier pass of this tile are not recomputed: they were copied to a
         // per-CTA cache in L2 (bulk store of the 32 KB operand stage) and are streamed back by a bulk load
         // that completes the stage's full barrier.  Every K* block is generated exactly once per tile.
-        const bool use_cache = !PAIR && !mo && prm.kcache != nullptr;
+        const bool use_cache = !mo && prm.kcache != nullptr;
         const int kb_cached = (use_cache && p > 0 && !(prm.dbg & 16)) ? last_kb(min(NSLOT * (p - 1) + NSLOT - 1, n_chunks - 1)) + 1 : 0;
         const bool store_cache = use_cache && (p + 1 < n_pass);
         unsigned char *kc = prm.kcache + (size_t)blockIdx.x * nkb * STAGE_BYTES;
@@ -573,9 +578,18 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
               // released: the other warps do not wait on a_empty here, so an arrival of their own could land
               // in the still-open phase of two K-blocks ago (its bulk load may not have completed yet)
               mbar_wait_prof(smem_u32(&a_empty[sa]), pa ^ 1, 32, w_aempty, pon);
-              mbar_expect_tx(smem_u32(&a_full[sa]), STAGE_BYTES);
-              mbar_arrive_n(smem_u32(&a_full[sa]), GEN_WARPS - 1);
-              bulk_load(smem_u32(sA + sa * STAGE_BYTES), kc + (size_t)kb * STAGE_BYTES, STAGE_BYTES, smem_u32(&a_full[sa]));
+              if (PAIR) {
+                // the stage lands in THIS CTA's shared memory, its bytes are counted on the leader's barrier
+                // (2-SM tensor load through a linear map of the cache: 256 rows of 128 B = one stage)
+                const uint32_t full = mapa_rank(smem_u32(&a_full[sa]), 0);
+                mbar_expect_tx_cluster(full, STAGE_BYTES);
+                mbar_arrive_n_cluster(full, GEN_WARPS - 1);
+                tma_load_2d_2sm(smem_u32(sA + sa * STAGE_BYTES), &map_kc, full, 0, (int)((blockIdx.x * nkb + kb) * 256));
+              } else {
+                mbar_expect_tx(smem_u32(&a_full[sa]), STAGE_BYTES);
+                mbar_arrive_n(smem_u32(&a_full[sa]), GEN_WARPS - 1);
+                bulk_load(smem_u32(sA + sa * STAGE_BYTES), kc + (size_t)kb * STAGE_BYTES, STAGE_BYTES, smem_u32(&a_full[sa]));
+              }
             }
             if (++sa == NSTA) { sa = 0; pa ^= 1; }
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -762,10 +776,25 @@ static int make_b_map(CUtensorMap *map, const void *base, int n_pad, int box_row
   return OMBO_OK;
 }
 
+// the K* cache seen as rows of 128 B (one shared-memory stage = 256 rows), no swizzle: a straight copy
+static int make_linear_map(CUtensorMap *map, const void *base, size_t rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { ombo_set_error("cuTensorMapEncodeTiled is not available from the driver"); return OMBO_ERR_CUDA; }
+  cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, 256};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { ombo_set_error("cuTensorMapEncodeTiled (cache) failed (%d)", (int)r); return OMBO_ERR_CUDA; }
+  return OMBO_OK;
+}
+
 int ombo_fast_path_built() { return 1; }
 
 template <int DP, int R, int MODE, int GW>
-static int launch_fast(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensorMap &map_lo, const FastParams &prm,
+static int launch_fast(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensorMap &map_lo, const CUtensorMap &map_kc, const FastParams &prm,
                        int grid, int cs, cudaStream_t s) {
   const size_t smem = (size_t)6 * STAGE_BYTES + (size_t)DP * FM * 4 + 2 * (size_t)(DP + 2) * FK * 4 +
                       8 * FM * 4 + 16 + (2 * 3 + 2 * 4 + 8) * 8 + 16 + 1024;
@@ -785,7 +814,7 @@ static int launch_fast(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensorM
   at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  OMBO_CUDA(cudaLaunchKernelEx(&cfg, k_posterior_fast<DP, R, MODE, GW>, map_hi, map_lo, prm));
+  OMBO_CUDA(cudaLaunchKernelEx(&cfg, k_posterior_fast<DP, R, MODE, GW>, map_hi, map_lo, map_kc, prm));
   return OMBO_OK;
 }
 
@@ -823,21 +852,27 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
   grid = (grid + cs - 1) / cs * cs;            // whole clusters; surplus CTAs run a dummy tile
   if (grid > ctx->num_sms) grid = ctx->num_sms / cs * cs;
   prm.kcache = nullptr;
-  if (!pair && want_var && gp.n_pad > (wide ? 512 : 512) && !getenv("OMBO_FAST_NOCACHE")) {   // more than one TMEM pass
+  CUtensorMap map_kc = map_hi;                 // placeholder unless the pair variant reloads through it
+  if (want_var && gp.n_pad > 512 && !getenv("OMBO_FAST_NOCACHE")) {   // more than one TMEM pass
     rc = ombo_ws_reserve(&ctx->ws_scratch, &ctx->ws_scratch_bytes, (size_t)grid * (gp.n_pad / FK) * STAGE_BYTES);
     if (rc) return rc;
     prm.kcache = (unsigned char *)ctx->ws_scratch;
     if (getenv("OMBO_FAST_ZEROCACHE")) OMBO_CUDA(cudaMemsetAsync(prm.kcache, 0, (size_t)grid * (gp.n_pad / FK) * STAGE_BYTES, s));
+    if (pair) {
+      rc = make_linear_map(&map_kc, prm.kcache, (size_t)grid * (gp.n_pad / FK) * 256);
+      if (rc) return rc;
+    }
   }
   const int d = gp.d;
   bool gw16 = false;
   { const char *e = getenv("OMBO_FAST_GW"); if (e && atoi(e) == 16) gw16 = true; }
 #define FAST_DISPATCH(DPV, RV)                                                                  \
-  rc = pair ? launch_fast<DPV, RV, 1, 8>(ctx, map_hi, map_lo, prm, grid, cs, s)                   \
-     : (wide && gw16 && RV == 4) ? launch_fast<DPV, 2, 2, 16>(ctx, map_hi, map_lo, prm, grid, cs, s) \
-     : wide ? launch_fast<DPV, RV, 2, 8>(ctx, map_hi, map_lo, prm, grid, cs, s)                   \
-     : (gw16 && RV == 4) ? launch_fast<DPV, 2, 0, 16>(ctx, map_hi, map_lo, prm, grid, cs, s)       \
-                         : launch_fast<DPV, RV, 0, 8>(ctx, map_hi, map_lo, prm, grid, cs, s)
+  rc = (pair && gw16 && RV == 4) ? launch_fast<DPV, 2, 1, 16>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s) \
+     : pair ? launch_fast<DPV, RV, 1, 8>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)                   \
+     : (wide && gw16 && RV == 4) ? launch_fast<DPV, 2, 2, 16>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s) \
+     : wide ? launch_fast<DPV, RV, 2, 8>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)                   \
+     : (gw16 && RV == 4) ? launch_fast<DPV, 2, 0, 16>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)       \
+                         : launch_fast<DPV, RV, 0, 8>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)
   if (d <= 2) { FAST_DISPATCH(2, 4); }
   else if (d <= 4) { FAST_DISPATCH(4, 4); }
   else if (d <= 6) { FAST_DISPATCH(6, 4); }

@@ -13,13 +13,17 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
 #define MMA(QUAL, d, a, b, i, acc)                                                                        \
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16" QUAL          \
                " [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(a), "l"(b), "r"(i), "r"(acc) : "memory")
+#define MMA_TS(d, a, b, i, acc)                                                                          \
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16"                 \
+               " [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a), "l"(b), "r"(i), "r"(acc) : "memory")
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
   asm volatile("{\n.reg .pred P1;\nelect.sync _|P1, 0xffffffff;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(pred));
   return pred;
 }
 extern __shared__ __align__(1024) unsigned char sm[];
-__global__ void __launch_bounds__(128, 1) k(int pattern, int n_mma, int N, long long *out) {
+template <int pattern>
+__global__ void __launch_bounds__(128, 1) k(int n_mma, int N, long long *out) {
   __shared__ uint64_t bar;
   __shared__ uint32_t tslot;
   unsigned char *base = sm + ((1024u - (smem_u32(sm) & 1023u)) & 1023u);
@@ -42,6 +46,7 @@ __global__ void __launch_bounds__(128, 1) k(int pattern, int n_mma, int N, long 
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t a0 = smem_u32(base), b0 = smem_u32(base + 32 * 1024);
     long long t0 = clock64();
+#pragma unroll 12
     for (int i = 0; i < n_mma; ++i) {
       const int ks = i & 3;
       uint32_t d = tm;
@@ -51,7 +56,9 @@ __global__ void __launch_bounds__(128, 1) k(int pattern, int n_mma, int N, long 
       if (pattern == 6) { b = b0 + ((i / 4) % 3) * 32 * 1024 + ks * 32; }   // 3 different B tiles, same accumulator
       if (pattern == 7) { a = a0 + ((i >> 2) & 1) * 16 * 1024 + ks * 32; }
       const uint64_t da = make_sdesc(a), db = make_sdesc(b);
-      if (pattern == 4) { if (i & 1) MMA(".collector::a::lastuse", d, da, db, idesc, 1u); else MMA(".collector::a::fill", d, da, db, idesc, 1u); }
+      if (pattern == 8) { MMA_TS(tm, tm + 256 + ((i >> 2) & 3) * 64 + ks * 8, db, idesc, 1u); }   // A operand in TMEM
+      else if (pattern == 9) { MMA_TS(tm + ((i / 12) & 1) * 128, tm + 256 + ((i >> 2) & 3) * 64 + ks * 8, make_sdesc(b0 + ((i / 4) % 3) * 32 * 1024 + ks * 32), idesc, 1u); }
+      else if (pattern == 4) { if (i & 1) MMA(".collector::a::lastuse", d, da, db, idesc, 1u); else MMA(".collector::a::fill", d, da, db, idesc, 1u); }
       else MMA("", d, da, db, idesc, 1u);
     }
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar)) : "memory");
@@ -63,19 +70,37 @@ __global__ void __launch_bounds__(128, 1) k(int pattern, int n_mma, int N, long 
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tm), "r"(512u));
 }
+template <int P>
+static void launch1(int grid, int n_mma, int N, long long *out) {
+  cudaFuncSetAttribute(k<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  k<P><<<grid, 128, 200 * 1024>>>(n_mma, N, out);
+}
+static void launch(int pattern, int grid, int n_mma, int N, long long *out) {
+  switch (pattern) {
+    case 0: launch1<0>(grid, n_mma, N, out); break;
+    case 1: launch1<1>(grid, n_mma, N, out); break;
+    case 2: launch1<2>(grid, n_mma, N, out); break;
+    case 4: launch1<4>(grid, n_mma, N, out); break;
+    case 6: launch1<6>(grid, n_mma, N, out); break;
+    case 7: launch1<7>(grid, n_mma, N, out); break;
+    case 8: launch1<8>(grid, n_mma, N, out); break;
+    case 9: launch1<9>(grid, n_mma, N, out); break;
+  }
+}
 int main() {
   long long *out;
   cudaMalloc(&out, 148 * 8);
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int n_mma = 12000;
   struct { int pattern, N; const char *name; } cases[] = {
       {0, 128, "same accumulator, N=128"}, {0, 256, "same accumulator, N=256"}, {0, 64, "same accumulator, N=64"},
       {1, 128, "alternate 2 accumulators each MMA, N=128"}, {2, 128, "switch accumulator every 12, N=128"},
       {4, 128, "same accumulator, A keep/reuse pairs, N=128"}, {6, 128, "same accumulator, 3 B tiles, N=128"},
-      {7, 128, "same accumulator, 2 A tiles, N=128"}};
+      {7, 128, "same accumulator, 2 A tiles, N=128"},
+      {8, 128, "A in TMEM, N=128"}, {8, 256, "A in TMEM, N=256"}, {8, 64, "A in TMEM, N=64"},
+      {9, 128, "A in TMEM, 2 accumulators, 3 B tiles, N=128"}};
   for (auto &c : cases) {
     for (int grid : {1, 148}) {
-      k<<<grid, 128, 200 * 1024>>>(c.pattern, n_mma, c.N, out);
+      launch(c.pattern, grid, n_mma, c.N, out);
       cudaError_t e = cudaDeviceSynchronize();
       long long h[148];
       cudaMemcpy(h, out, grid * 8, cudaMemcpyDeviceToHost);
