@@ -403,6 +403,46 @@ def test_posterior_fast_vs_oracle(n, d, m):
         assert torch.equal(mu_b[0].cpu(), torch.as_tensor(mu)) and torch.equal(var_b[0].cpu(), torch.as_tensor(var))
 
 
+@pytest.mark.parametrize("mode", ["1", "2", "4"])
+def test_posterior_fast_kernel_variants(mode, monkeypatch):
+    """The variants kept selectable next to the default kernel (128-column single CTA, coupled
+    cta_group::2 pair, decoupled pair) answer within the same tolerance -- ragged m, one to three
+    TMEM passes, n_pad = 128 (two K-blocks: shorter than the operand ring)."""
+    if not _cabi.fast_path_available():
+        pytest.skip("fast path not built")
+    monkeypatch.setenv("OMBO_FAST_MODE", mode)
+    for n, d, m in ((100, 4, 129), (512, 12, 3000), (1024, 10, 148 * 128 * 2 + 77), (1536, 7, 2048)):
+        X, Y, ells, sf2 = make_problem(n, d)
+        gp = ob.GPModel(X, Y[:, 0], ells[0], sf2[0], device=DEV)
+        st = O.gp_fit_state(X, Y[:, 0], ells[0], sf2[0])
+        Xc = np.random.default_rng(n + d).random((m, d))
+        sel = np.random.default_rng(1).integers(0, m, min(m, 3000))
+        mu_o, var_o = O.gp_posterior(st, Xc[sel])
+        mu, var = ob.posterior([gp], Xc, precision="fast")
+        mu, var = mu[0].cpu().numpy(), var[0].cpu().numpy()
+        np.testing.assert_allclose(mu[sel], mu_o, rtol=1e-3, atol=1e-3 * np.abs(mu_o).max())
+        np.testing.assert_allclose(np.sqrt(var[sel]), np.sqrt(var_o), rtol=1e-3, atol=1e-3 * np.sqrt(sf2[0]))
+        mu_b, var_b = ob.posterior([gp], Xc, precision="fast")
+        assert torch.equal(mu_b[0].cpu(), torch.as_tensor(mu)) and torch.equal(var_b[0].cpu(), torch.as_tensor(var))
+    # mean-only launches (the acquisition never reads this model's variance) and d > 12 (mode 4 falls back)
+    X, Y, ells, sf2 = make_problem(300, 16)
+    gp = ob.GPModel(X, Y[:, 0], ells[0] * 2.0, sf2[0], device=DEV)
+    st = O.gp_fit_state(X, Y[:, 0], ells[0] * 2.0, sf2[0])
+    Xc = np.random.default_rng(3).random((1000, 16))
+    mu_o, var_o = O.gp_posterior(st, Xc)
+    mu, var = ob.posterior([gp], Xc, precision="fast")
+    np.testing.assert_allclose(np.sqrt(var[0].cpu().numpy()), np.sqrt(var_o), rtol=2e-3, atol=2e-3 * np.sqrt(sf2[0]))
+    # reference semantics never reads model 1's variance: that GP runs the kernel's mean-only path
+    X, Y, ells, sf2 = make_problem(640, 6)
+    models = [ob.GPModel(X, Y[:, i], ells[i], sf2[i], device=DEV) for i in range(2)]
+    spec = ob.spec_ehvi(Y.max(0), ob.host_prep.calc_pf(Y), ob.host_prep.cached_samples(2, 5, seed=0), "reference")
+    pool = ob.CandidatePool.counter(5000, np.zeros(6), np.ones(6), seed=4)
+    fast = ob.score(models, spec, pool, precision="fast", want_acq=True)
+    ref = ob.score(models, spec, pool, precision="fp64", want_acq=True)
+    a_f, a_r = fast.acq.cpu().numpy(), ref.acq.cpu().numpy()
+    np.testing.assert_allclose(a_f, a_r, rtol=5e-3, atol=2e-3 * np.abs(a_r).max())
+
+
 def test_posterior_fast_rbf_and_high_dim():
     if not _cabi.fast_path_available():
         pytest.skip("fast path not built")
