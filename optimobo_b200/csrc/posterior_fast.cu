@@ -236,14 +236,15 @@ extern __shared__ __align__(1024) unsigned char fast_smem[];
 // R    = candidate rows held in registers per generator thread (4 when DP <= 12, else 2)
 // PAIR = cta_group::2: two CTAs of a cluster form one UMMA M = 256 x N = 256 tile pair.  Each CTA generates
 //        the K* rows of its own 128 candidates and TMA-loads only ITS half of the B tile; the leader CTA
-//        issues the MMAs for both tensor cores.  Per MAC this halves the shared-memory operand traffic,
-//        which is what bounds the single-CTA variant (8 KB of operands per 128x128x16 MMA = the full
-//        128 B/clk of the SM's shared memory, before the TMA and K1 writes are even counted).
-// MODE = 0: single CTA, 128-column chunks (UMMA N = 128, 96.8 cycles each in SS mode)
-//        1: cta_group::2 pair (see above)
-//        2: single CTA, 256-column chunks (UMMA N = 256 at 160.8 cycles = 17 % fewer cycles per MAC; the
-//           diagonal K-blocks shrink N to 192 / 128 / 64), B ring entries are single planes so the lo
-//           plane of a unit can still be in flight while its hi plane is being multiplied
+//        issues the MMAs for both tensor cores.  Per MAC this halves the B traffic through shared memory.
+// The UMMA itself runs at its N/2-cycle floor in every mode (scripts/umma_bench.cu); what separates the
+// modes is shared-memory traffic per MAC (the A tile is re-read by every MMA: 64 B/clk at N = 128, 32 B/clk
+// at N = 256, on top of 64 B/clk of B reads and the TMA / K1 writes) and, at the power cap, issued work.
+// MODE = 0: single CTA, 128-column chunks
+//        1: cta_group::2 pair (see above; N cannot shrink on the diagonal K-blocks)
+//        2: single CTA, 256-column chunks (half the A re-reads per MAC; the diagonal K-blocks shrink N to
+//           192 / 128 / 64), B ring entries are single planes so the lo plane of a unit can still be in
+//           flight while its hi plane is being multiplied -- the default
 template <int DP, int R, int MODE, int GW>
 __global__ void __launch_bounds__((8 + GW) * 32, 1)
 k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
