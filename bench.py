@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fit", action="store_true", help="skip the (untimed, separately reported) device hyper-parameter fit")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -206,7 +207,7 @@ def main():
 
     # hyper-parameter fit on the device (section 8f-1): reported separately, not part of the metric
     fit_ms = None
-    if rank == 0:
+    if rank == 0 and not args.no_fit:
         from optimobo_b200.fit import fit_hyperparameters_device
         t0 = time.perf_counter()
         fit_hyperparameters_device(X, Y[:, 0], max_f_eval=40, device=dev)
