@@ -14,6 +14,7 @@ import optimobo_b200.scalarisations as sc  # noqa: E402
 from optimobo_b200.algorithms import (EMO, KEEP, MonoSurrogateOptimiser, MultiSurrogateOptimiser, ParEGO,  # noqa: E402
                                       ParEGO_C1, ParEGO_C2)
 from optimobo_b200.problem import ElementwiseProblem, Problem  # noqa: E402
+from oracle import oracle as O  # noqa: E402
 
 
 class MyProblem(ElementwiseProblem):     # README example 1 (BASELINE config 1)
@@ -171,3 +172,53 @@ def test_nccl_two_ranks_agree_with_single_gpu():
                           os.path.join(root, "scripts", "check_multigpu.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "multi-GPU check ok" in out.stdout
+
+
+# ------------------------------------------------------------------------------------------
+# C1: the whole outer loop against an oracle twin.  With injected
+# hyper-parameters, FP64 scoring, no refinement and the counter-generated pool (bit-identical on
+# host and device) the GPU optimiser and a numpy loop built from oracle/ functions must propose
+# the SAME points, so evaluated samples and hypervolume trajectories coincide.
+# ------------------------------------------------------------------------------------------
+class ReadmeProblem(Problem):
+    def __init__(self):
+        super().__init__(n_var=2, n_obj=2, xl=np.array([-2.0, -2.0]), xu=np.array([2.0, 2.0]))
+
+    def _evaluate(self, x, out, *args, **kwargs):
+        out["F"] = [100 * (x[:, 0] ** 2 + x[:, 1] ** 2), (x[:, 0] - 1) ** 2 + x[:, 1] ** 2]
+
+
+def _oracle_twin_ehvi(problem, seed, budget, n_init, sample_exponent, m, hyper, max_point):
+    rng = np.random.default_rng(seed)
+    ranges = list(zip(problem.xl, problem.xu))
+    X = ob.host_prep.latin_hypercube(n_init, ranges, rng)
+    Y = np.asarray([problem.evaluate(x) for x in X])
+    cache = ob.host_prep.cached_samples(2, sample_exponent, seed=int(rng.integers(0, 2 ** 31)))
+    n_dirs = len(O.das_dennis(100, 2))
+    hv = []
+    for _ in range(budget):
+        hv.append(O.hypervolume(Y, max_point))
+        rng.integers(0, n_dirs)                                     # the reference draws a direction every iteration
+        states = [O.gp_fit_state(X, Y[:, i], hyper[0], hyper[1]) for i in range(2)]
+        pool_seed = int(rng.integers(1, 2 ** 62))
+        Xc = O.candidates_from_counter(pool_seed, 0, m, problem.xl, problem.xu)
+        (mu0, v0), (mu1, v1) = [O.gp_posterior(s, Xc) for s in states]
+        acq = O.ehvi_batched(mu0, mu1, v0, v1, O.calc_pf(Y), np.asarray(max_point, float), cache, "reference")
+        x = Xc[O.argmax_lowest_index(acq)]
+        X, Y = np.vstack((X, x)), np.vstack((Y, problem.evaluate(x)))
+    return X, Y, hv
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4])
+def test_c1_solve_trajectory_matches_oracle_twin(seed):
+    problem, max_point = ReadmeProblem(), [700.0, 12.0]
+    hyper = (np.array([1.5, 1.5]), 4000.0)
+    budget, n_init, m = 5, 12, 1 << 12
+    opt = MultiSurrogateOptimiser(problem, [0, 0], max_point, n_candidates=m, precision="fp64",
+                                                semantics="reference", seed=seed, hyperparameters=hyper,
+                                                refine_rounds=0)
+    res = opt.solve(budget=budget, n_init_samples=n_init, sample_exponent=3)
+    Xo, Yo, hvo = _oracle_twin_ehvi(problem, seed, budget, n_init, 3, m, hyper, max_point)
+    np.testing.assert_allclose(res.Xsample, Xo, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(res.ysample, Yo, rtol=1e-12)
+    np.testing.assert_allclose(res.hypervolume_convergence, hvo, rtol=1e-12)
