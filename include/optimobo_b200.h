@@ -192,6 +192,23 @@ int ombo_pool_rows(ombo_ctx *ctx, const ombo_pool *pool, int64_t index, int64_t 
  * DEVICE int64; it can be the NCCL send buffer itself.  Requires 0 <= index < 2^32. */
 int ombo_pack_key(ombo_ctx *ctx, const ombo_best *best_dev, int64_t *key_dev, void *stream);
 
+/* ---- candidate-independent prep on the device ----------------------
+ * Replaces the reference's pygmo / pymoo calls of every BO iteration; all pointers are DEVICE float64
+ * row-major unless noted, results are bit-identical to optimobo_b200/host_prep.py.
+ *
+ * ombo_pareto_mask: mask[j] = 1 iff row j of Y (n,k) is in the first non-dominated front (minimisation;
+ *   pygmo.fast_non_dominated_sorting(...)[0][0], util_functions.py:64-77).  1 <= k <= 8.
+ * ombo_hypervolume: exact dominated hypervolume of P (p,k), k = 2 or 3, w.r.t. ref (HOST, k doubles);
+ *   points beyond ref contribute nothing (pymoo HV optimisers.py:217-219; pygmo hypervolume.compute
+ *   util_functions.py:198-199).  hv_out: DEVICE double[1].  p <= 16384.
+ * ombo_cells_2d: the (p+1, 2, 2) cell decomposition of a 2-D front EMO scores against
+ *   (emo.py:55-152): [c][0] = upper, [c][1] = lower corner.  ideal / maxp: HOST double[2].  p >= 1. */
+int ombo_pareto_mask(ombo_ctx *ctx, const double *Y, int n, int k, unsigned char *mask, void *stream);
+int ombo_hypervolume(ombo_ctx *ctx, const double *P, int p, int k, const double *ref, double *hv_out,
+                     void *stream);
+int ombo_cells_2d(ombo_ctx *ctx, const double *PF, int p, const double *ideal, const double *maxp,
+                  double *cells, void *stream);
+
 /* Per-kernel timing of the dominant (posterior) kernel with CUDA events recorded on the
  * launching stream: enable, run, synchronise, then read the launch count and total duration. */
 int ombo_profile_enable(ombo_ctx *ctx, int enable);

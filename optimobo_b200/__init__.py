@@ -4,7 +4,7 @@ Batched GP posterior (Matern-5/2 / RBF ARD) + multi-objective acquisition + arg-
 large candidate pools as hand-written sm_100a CUDA behind a C ABI (include/optimobo_b200.h),
 dropped in under the reference's Python surface.  See DESIGN.md / INTEGRATION.md.
 """
-from . import _cabi, host_prep, scalarisations  # noqa: F401
+from . import _cabi, device_prep, host_prep, scalarisations  # noqa: F401
 from .gp import GPModel  # noqa: F401
 from .acquisition import (  # noqa: F401
     AcquisitionSpec, CandidatePool, EHVI, EHVI_3D, acquire_from_posterior, consraint_ei, evaluate,

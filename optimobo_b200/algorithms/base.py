@@ -17,7 +17,7 @@ import time
 
 import numpy as np
 
-from .. import host_prep
+from .. import device_prep, host_prep
 from ..acquisition import CandidatePool, propose
 from ..fit import fit_hyperparameters, fit_hyperparameters_device
 from ..gp import GPModel
@@ -26,7 +26,7 @@ from ..gp import GPModel
 class PoolOptimiserBase:
     def __init__(self, test_problem, ideal_point=None, max_point=None, n_candidates=1 << 16, precision="auto",
                  semantics="reference", device="cuda:0", seed=None, hyperparameters=None, max_f_eval=1000,
-                 fit_on_device=True, refine_rounds=2):
+                 fit_on_device=True, refine_rounds=2, prep_on_device="auto"):
         self.test_problem = test_problem
         self.max_point = max_point
         self.ideal_point = ideal_point
@@ -46,6 +46,9 @@ class PoolOptimiserBase:
         self.max_f_eval = max_f_eval
         self.fit_on_device = fit_on_device       # likelihood + gradient on the GPU (ombo_gp_nlml_grad)
         self.refine_rounds = refine_rounds       # zoom rounds around the pool winner (DE's polish step)
+        # first front / hypervolume / cells on the device (bit-identical to host_prep; "auto": once the sample
+        # holds >= 512 rows, where the O(n^2) host versions start to show next to a ~100 ms scoring pass)
+        self.prep_on_device = prep_on_device
         self.timings = []
 
     # ---- problem access ------------------------------------------------------------------------
@@ -73,8 +76,19 @@ class PoolOptimiserBase:
         if changed and scalarisation is not None:
             scalarisation.set_bounds(self.ideal_point, self.max_point)
 
+    def _prep_device(self, rows):
+        return self.prep_on_device is True or (self.prep_on_device == "auto" and rows >= 512)
+
     def _hypervolume(self, ysample, ref_point=None):
-        return host_prep.hypervolume(ysample, self.max_point if ref_point is None else ref_point)
+        ref = self.max_point if ref_point is None else ref_point
+        if self._prep_device(len(ysample)) and np.shape(ysample)[1] in (2, 3):
+            return device_prep.hypervolume(ysample, ref, self.device)
+        return host_prep.hypervolume(ysample, ref)
+
+    def _calc_pf(self, ysample):
+        if self._prep_device(len(ysample)):
+            return device_prep.calc_pf(ysample, self.device)
+        return host_prep.calc_pf(ysample)
 
     # ---- surrogate ---------------------------------------------------------------------------------
     def _fit_model(self, X, y):
@@ -116,5 +130,7 @@ class PoolOptimiserBase:
     # ---- result ------------------------------------------------------------------------------------
     @staticmethod
     def _pareto_members(ysample):
-        mask = host_prep.pareto_mask(ysample) if len(ysample) > 1 else np.ones(len(ysample), bool)
+        if len(ysample) <= 1:
+            return np.ones(len(ysample), bool)
+        mask = host_prep.pareto_mask(ysample)
         return mask

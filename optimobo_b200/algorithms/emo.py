@@ -16,6 +16,10 @@ class EMO(PoolOptimiserBase):
             raise ValueError("EMO's cell decomposition is 2-objective only (emo.py:21)")
 
     def decompose_into_cells(self, data_points):
+        if self._prep_device(len(data_points)):
+            from .. import device_prep
+            return device_prep.decompose_into_cells(data_points, self.ideal_point, self.max_point,
+                                                    self.device).cpu().numpy()
         return host_prep.decompose_into_cells(data_points, self.ideal_point, self.max_point)
 
     def solve(self, budget=100, n_init_samples=5):
@@ -26,7 +30,7 @@ class EMO(PoolOptimiserBase):
             self._update_bounds(ysample)
             hypervolume_convergence.append(self._hypervolume(ysample))
             models = [self._fit_model(Xsample, ysample[:, i]) for i in range(self.n_obj)]
-            cells = self.decompose_into_cells(host_prep.calc_pf(ysample))
+            cells = self.decompose_into_cells(self._calc_pf(ysample))
             X_next, _ = self._propose(models, spec_hv_poi(cells))
             y_next = self._objective_function(problem, X_next)
             ysample = np.vstack((ysample, y_next))

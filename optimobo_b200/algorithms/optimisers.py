@@ -29,7 +29,7 @@ class MultiSurrogateOptimiser(PoolOptimiserBase):
             models = [self._fit_model(Xsample, ysample[:, i]) for i in range(problem.n_obj)]
             ref_dir = np.asarray(ref_dirs[self.rng.integers(0, len(ref_dirs))])
             if acquisition_func is None:
-                pf = host_prep.calc_pf(ysample)
+                pf = self._calc_pf(ysample)
                 if problem.n_obj == 2:
                     spec = spec_ehvi(self.max_point, pf, cached_samples, self.semantics)
                 else:

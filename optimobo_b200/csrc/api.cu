@@ -348,6 +348,29 @@ int ombo_pack_key(ombo_ctx *ctx, const ombo_best *best_dev, int64_t *key_dev, vo
   return ombo_pack_key_impl(ctx, best_dev, (long long *)key_dev, (cudaStream_t)stream);
 }
 
+int ombo_pareto_mask(ombo_ctx *ctx, const double *Y, int n, int k, unsigned char *mask, void *stream) {
+  OMBO_CHECK(ctx && Y && mask, "pareto_mask: NULL argument");
+  OMBO_CHECK(n >= 1 && k >= 1 && k <= 8, "pareto_mask: need n >= 1 and 1 <= k <= 8 (got n=%d k=%d)", n, k);
+  OMBO_CUDA(cudaSetDevice(ctx->device));
+  return ombo_pareto_mask_impl(ctx, Y, n, k, mask, (cudaStream_t)stream);
+}
+
+int ombo_hypervolume(ombo_ctx *ctx, const double *P, int p, int k, const double *ref, double *hv_out, void *stream) {
+  OMBO_CHECK(ctx && ref && hv_out && (P || p == 0), "hypervolume: NULL argument");
+  OMBO_CHECK(k == 2 || k == 3, "hypervolume: 2 or 3 objectives (got %d)", k);
+  OMBO_CHECK(p >= 0 && p <= 16384, "hypervolume: 0 <= p <= 16384 (got %d)", p);
+  OMBO_CUDA(cudaSetDevice(ctx->device));
+  return ombo_hypervolume_impl(ctx, P, p, k, ref, hv_out, (cudaStream_t)stream);
+}
+
+int ombo_cells_2d(ombo_ctx *ctx, const double *PF, int p, const double *ideal, const double *maxp, double *cells,
+                  void *stream) {
+  OMBO_CHECK(ctx && PF && ideal && maxp && cells, "cells_2d: NULL argument");
+  OMBO_CHECK(p >= 1 && p <= 16384, "cells_2d: 1 <= p <= 16384 (got %d)", p);
+  OMBO_CUDA(cudaSetDevice(ctx->device));
+  return ombo_cells_2d_impl(ctx, PF, p, ideal, maxp, cells, (cudaStream_t)stream);
+}
+
 int ombo_profile_enable(ombo_ctx *ctx, int enable) {
   OMBO_CHECK(ctx != nullptr, "profile_enable: NULL ctx");
   OMBO_CUDA(cudaSetDevice(ctx->device));

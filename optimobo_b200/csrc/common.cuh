@@ -154,5 +154,10 @@ int ombo_acquire(ombo_ctx *ctx, const ombo_acq *acq, int n_gp, const double *mu,
                  ombo_best *best_dev, cudaStream_t s);
 int ombo_best_init(ombo_ctx *ctx, ombo_best *best_dev, cudaStream_t s);
 int ombo_pack_key_impl(ombo_ctx *ctx, const ombo_best *best_dev, long long *key_dev, cudaStream_t s);
+// front_prep.cu
+int ombo_pareto_mask_impl(ombo_ctx *ctx, const double *Y, int n, int k, unsigned char *mask, cudaStream_t s);
+int ombo_hypervolume_impl(ombo_ctx *ctx, const double *P, int p, int k, const double *ref, double *out, cudaStream_t s);
+int ombo_cells_2d_impl(ombo_ctx *ctx, const double *PF, int p, const double *ideal, const double *maxp, double *cells,
+                       cudaStream_t s);
 int ombo_pool_rows_impl(ombo_ctx *ctx, const PoolDev &pool, long long first, long long count,
                         double *out, cudaStream_t s);

@@ -222,3 +222,23 @@ def test_c1_solve_trajectory_matches_oracle_twin(seed):
     np.testing.assert_allclose(res.Xsample, Xo, rtol=0, atol=1e-12)
     np.testing.assert_allclose(res.ysample, Yo, rtol=1e-12)
     np.testing.assert_allclose(res.hypervolume_convergence, hvo, rtol=1e-12)
+
+
+def test_device_prep_inside_solve_changes_nothing():
+    """prep_on_device=True (first front, hypervolume, cells on the GPU) gives the same run as the
+    host versions: the device kernels are bit-identical to host_prep."""
+    hyper = (np.array([1.5, 1.5]), 4000.0)
+    runs = []
+    for on_dev in (False, True):
+        opt = MultiSurrogateOptimiser(ReadmeProblem(), [0, 0], [700.0, 12.0], n_candidates=1 << 12,
+                                      precision="fp64", seed=3, hyperparameters=hyper, refine_rounds=0,
+                                      prep_on_device=on_dev)
+        runs.append(opt.solve(budget=4, n_init_samples=10, sample_exponent=3))
+    np.testing.assert_array_equal(runs[0].Xsample, runs[1].Xsample)
+    np.testing.assert_array_equal(runs[0].hypervolume_convergence, runs[1].hypervolume_convergence)
+    emo = []
+    for on_dev in (False, True):
+        opt = EMO(ReadmeProblem(), [0, 0], [700.0, 12.0], n_candidates=1 << 12, precision="fp64", seed=5,
+                  hyperparameters=hyper, refine_rounds=0, prep_on_device=on_dev)
+        emo.append(opt.solve(budget=3, n_init_samples=10))
+    np.testing.assert_array_equal(emo[0].Xsample, emo[1].Xsample)

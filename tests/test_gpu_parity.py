@@ -522,3 +522,61 @@ def test_device_fit_reaches_the_host_optimum():
     f_d = _nlml_and_grad(np.log(np.concatenate(([sf2_d], ell_d))), X, y, "matern52", 1e-8)[0]
     f_h = _nlml_and_grad(np.log(np.concatenate(([sf2_h], ell_h))), X, y, "matern52", 1e-8)[0]
     assert abs(f_d - f_h) <= 1e-3 * abs(f_h) + 1e-3
+
+
+# ------------------------------------------------------------------------------------------
+# candidate-independent prep on the device
+# (first front, exact 2-D / 3-D hypervolume, 2-D cell decomposition)
+# ------------------------------------------------------------------------------------------
+def test_device_prep_anchors():
+    """Hand-checkable values of SURVEY section 8c."""
+    front = np.array([[.1, .9], [.4, .5], [.8, .2]])
+    assert ob.device_prep.hypervolume(front, [1, 1], DEV) == pytest.approx(0.39, abs=1e-15)
+    cells = ob.device_prep.decompose_into_cells(front, [0, 0], [1, 1], DEV).cpu().numpy()
+    want = np.array([[[.1, 1], [0, 0]], [[.4, .9], [.1, 0]], [[.8, .5], [.4, 0]], [[1, .2], [.8, 0]]])
+    np.testing.assert_array_equal(cells, want)
+    assert ob.device_prep.hypervolume(np.zeros((0, 2)), [1, 1], DEV) == 0.0
+    assert ob.device_prep.hypervolume([[2.0, 0.5]], [1, 1], DEV) == 0.0           # beyond the reference point
+    assert ob.device_prep.hypervolume([[0.25, 0.5, 0.5]], [1, 1, 1], DEV) == pytest.approx(0.75 * 0.5 * 0.5)
+
+
+@pytest.mark.parametrize("n,k", [(1, 2), (2, 2), (57, 2), (300, 3), (1024, 2), (1500, 3), (4096, 2), (700, 5)])
+def test_device_pareto_front_matches_host_and_oracle(n, k):
+    rng = np.random.default_rng(n + k)
+    Y = rng.random((n, k))
+    Y[rng.integers(0, n, n // 8)] = Y[rng.integers(0, n, n // 8)]     # exact duplicates
+    Y[:, 0] = np.round(Y[:, 0], 2)                                     # ties in one objective
+    mask = ob.device_prep.pareto_mask(Y, DEV).cpu().numpy()
+    np.testing.assert_array_equal(mask, ob.host_prep.pareto_mask(Y))
+    np.testing.assert_array_equal(ob.device_prep.calc_pf(Y, DEV), O.calc_pf(Y))
+
+
+@pytest.mark.parametrize("n,k", [(5, 2), (120, 2), (1024, 2), (3000, 2), (40, 3), (400, 3), (1024, 3)])
+def test_device_hypervolume_matches_host_and_oracle(n, k):
+    rng = np.random.default_rng(10 * n + k)
+    Y = rng.random((n, k)) ** 2
+    Y[: n // 10] = Y[n // 10: 2 * (n // 10)]                            # duplicates
+    Y[:, -1] = np.round(Y[:, -1], 2)                                    # ties in the slicing objective
+    ref = np.full(k, 0.9)                                               # some points beyond the reference point
+    hv = ob.device_prep.hypervolume(Y, ref, DEV)
+    assert hv == ob.host_prep.hypervolume(Y, ref)                       # same order of operations: bit-identical
+    assert hv == pytest.approx(O.hypervolume(Y, ref), rel=1e-12)
+    # size-independent property: hypervolume of the whole sample = hypervolume of its first front
+    assert hv == pytest.approx(ob.device_prep.hypervolume(ob.device_prep.calc_pf(Y, DEV), ref, DEV), rel=1e-12)
+
+
+@pytest.mark.parametrize("n", [1, 2, 33, 500])
+def test_device_cells_match_host_oracle_and_feed_hv_poi(n):
+    rng = np.random.default_rng(n)
+    Y = rng.random((max(n * 6, 4), 2))
+    pf = ob.host_prep.calc_pf(Y)[:n] if n > 1 else Y[:1]
+    ideal, maxp = np.array([-0.1, -0.2]), np.array([1.1, 1.3])
+    cells = ob.device_prep.decompose_into_cells(pf, ideal, maxp, DEV)
+    np.testing.assert_array_equal(cells.cpu().numpy(), ob.host_prep.decompose_into_cells(pf, ideal, maxp))
+    np.testing.assert_array_equal(cells.cpu().numpy(), O.decompose_into_cells_2d(pf, ideal, maxp))
+    # the device cells drive the EMO acquisition exactly like the host ones
+    m = 257
+    mu, var = rng.random((2, m)), 0.01 + rng.random((2, m))
+    a_dev, _, _ = ob.acquire_from_posterior(ob.spec_hv_poi(cells.cpu().numpy()), mu, var, device=DEV)
+    a_ora = O.hv_poi_batched(mu.T, var.T, O.decompose_into_cells_2d(pf, ideal, maxp))
+    np.testing.assert_allclose(a_dev.cpu().numpy(), a_ora, rtol=1e-9, atol=1e-300)
