@@ -664,16 +664,13 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
     }
   }
   const int d = gp.d;
-  bool gw16 = false;
-  { const char *e = getenv("OMBO_FAST_GW"); if (e && atoi(e) == 16) gw16 = true; }
+  // (16 generator warps with 2 rows per lane were measured too: the same number of independent chains per
+  // scheduler, no gain -- the instantiations were dropped to keep the build short)
 #define FAST_DISPATCH(DPV, RV)                                                                  \
-  rc = dc ? ombo_launch_fast_dc(ctx, map_hi, map_lo, map_kc, prm, grid, s)                    \
-     : (pair && gw16 && RV == 4) ? launch_fast<DPV, 2, 1, 16>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s) \
-     : pair ? launch_fast<DPV, RV, 1, 8>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)                   \
-     : (wide && gw16 && RV == 4) ? launch_fast<DPV, 2, 2, 16>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s) \
-     : wide ? launch_fast<DPV, RV, 2, 8>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)                   \
-     : (gw16 && RV == 4) ? launch_fast<DPV, 2, 0, 16>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)       \
-                         : launch_fast<DPV, RV, 0, 8>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)
+  rc = dc ? ombo_launch_fast_dc(ctx, map_hi, map_lo, map_kc, prm, grid, s)                        \
+     : pair ? launch_fast<DPV, RV, 1, 8>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)           \
+     : wide ? launch_fast<DPV, RV, 2, 8>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)           \
+            : launch_fast<DPV, RV, 0, 8>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)
   if (d <= 2) { FAST_DISPATCH(2, 4); }
   else if (d <= 4) { FAST_DISPATCH(4, 4); }
   else if (d <= 6) { FAST_DISPATCH(6, 4); }
