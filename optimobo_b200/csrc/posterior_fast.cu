@@ -121,12 +121,23 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
           for (int kb = 0; kb < kb_end; ++kb) {
             for (int c = max(c_first, kb >> KSH); c <= c_last; ++c) {
               if (WIDE) {                    // two ring entries per unit: the hi plane, then the lo plane
+                // rows of the chunk above the diagonal band are never multiplied (the UMMA's N shrinks):
+                // on the diagonal K-blocks only the 64-row boxes from r0 on are fetched
+                // (a ragged last chunk keeps the per-plane maps: their out-of-bounds rows are zero-filled)
+                const int r0 = (prm.trim_b && (c + 1) * CW <= np) ? max(0, kb - 4 * c) * 64 : 0;
 #pragma unroll
                 for (int pl = 0; pl < 2; ++pl) {
                   mbar_wait_prof(smem_u32(&b_empty[st]), ph ^ 1, 64, w_bempty, pon);
                   const uint32_t full = smem_u32(&b_full[st]);
-                  mbar_expect_tx(full, STAGE_BYTES);
-                  tma_load_2d(smem_u32(sB + st * STAGE_BYTES), pl == 0 ? &map_hi : &map_lo, full, kb * FK, c * CW);
+                  const uint32_t dst = smem_u32(sB + st * STAGE_BYTES);
+                  if (r0 == 0) {
+                    mbar_expect_tx(full, STAGE_BYTES);
+                    tma_load_2d(dst, pl == 0 ? &map_hi : &map_lo, full, kb * FK, c * CW);
+                  } else {
+                    mbar_expect_tx(full, (uint32_t)((CW - r0) * 128));
+                    for (int rr = r0; rr < CW; rr += 64)       // map_kc: both planes as one (2 n_pad, n_pad) matrix, 64-row boxes
+                      tma_load_2d(dst + (uint32_t)(rr * 128), &map_kc, full, kb * FK, pl * np + c * CW + rr);
+                  }
                   if (++st == NSTB) { st = 0; ph ^= 1; }
                 }
                 continue;
@@ -556,10 +567,10 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int make_b_map(CUtensorMap *map, const void *base, int n_pad, int box_rows) {
+static int make_b_map(CUtensorMap *map, const void *base, int n_pad, int box_rows, int rows = 0) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { ombo_set_error("cuTensorMapEncodeTiled is not available from the driver"); return OMBO_ERR_CUDA; }
-  cuuint64_t dims[2] = {(cuuint64_t)n_pad, (cuuint64_t)n_pad};
+  cuuint64_t dims[2] = {(cuuint64_t)n_pad, (cuuint64_t)(rows ? rows : n_pad)};
   cuuint64_t strides[1] = {(cuuint64_t)n_pad * 2};
   cuuint32_t box[2] = {FK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
@@ -652,7 +663,15 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
   grid = (grid + cs - 1) / cs * cs;            // whole clusters; surplus CTAs run a dummy tile
   if (grid > ctx->num_sms) grid = ctx->num_sms / cs * cs;
   prm.kcache = nullptr;
-  CUtensorMap map_kc = map_hi;                 // placeholder unless the pair variant reloads through it
+  CUtensorMap map_kc = map_hi;                 // pair variants: linear map of the K* cache; wide: 64-row boxes of B
+  prm.trim_b = 0;
+  if (wide && (const unsigned char *)gp.blo == (const unsigned char *)gp.bhi + (size_t)gp.n_pad * gp.n_pad * 2 &&
+      !getenv("OMBO_FAST_NOTRIM")) {
+    // the two bf16 planes are adjacent in the state blob: one map over (2 n_pad, n_pad) serves both
+    rc = make_b_map(&map_kc, gp.bhi, gp.n_pad, 64, 2 * gp.n_pad);
+    if (rc) return rc;
+    prm.trim_b = 1;
+  }
   if (want_var && (dc || (gp.n_pad > 512 && !getenv("OMBO_FAST_NOCACHE")))) {   // dc: always; else only with > 1 TMEM pass
     rc = ombo_ws_reserve(&ctx->ws_scratch, &ctx->ws_scratch_bytes, (size_t)grid * (gp.n_pad / FK) * STAGE_BYTES);
     if (rc) return rc;

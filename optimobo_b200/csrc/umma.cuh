@@ -209,6 +209,7 @@ struct FastParams {
   unsigned char *kcache;   // per-CTA cache of generated K* blocks (n_pad/64 x 32 KB), L2 resident
   long long *prof;   // optional per-CTA wait-cycle counters (timing experiments)
   int mean_only;     // 1: this GP's variance is not read by the acquisition -> K1 + mean only, no MMA
+  int trim_b;        // 1: map_kc holds 64-row boxes of both B planes; diagonal K-blocks fetch only the rows they multiply
   int dbg;   // bit 0: skip the MMAs, bit 1: skip the K1 math (timing experiments only; results are garbage)
 };
 
