@@ -209,6 +209,16 @@ int ombo_hypervolume(ombo_ctx *ctx, const double *P, int p, int k, const double 
 int ombo_cells_2d(ombo_ctx *ctx, const double *PF, int p, const double *ideal, const double *maxp,
                   double *cells, void *stream);
 
+/* ---- joint posterior samples --------------------------------------------
+ * The device side of TuRBO's Thompson sampling, `GP.posterior_samples(X_cand, size=batch_size)`
+ * (turbo.py:75-117): out = mu + chol(K** - K*^T Ky^-1 K* + diag_add I) Z for the m candidates Xc (DEVICE f64
+ * (m,d) row-major), Z = DEVICE f64 (m,S) standard normals supplied by the caller, out DEVICE f64 (m,S).
+ * diag_add = likelihood noise + jitter.  FP64 throughout.  1 <= m <= 16384, S >= 1.  Returns OMBO_ERR_NOT_PD
+ * when the posterior covariance is not numerically positive definite (raise diag_add and retry).
+ * Synchronises the stream (status readback). */
+int ombo_posterior_joint_samples(ombo_ctx *ctx, const ombo_gp *gp, const double *Xc, int m, const double *Z,
+                                 int n_samples, double diag_add, double *out, void *stream);
+
 /* Per-kernel timing of the dominant (posterior) kernel with CUDA events recorded on the
  * launching stream: enable, run, synchronise, then read the launch count and total duration. */
 int ombo_profile_enable(ombo_ctx *ctx, int enable);

@@ -27,7 +27,7 @@ EXPORTS = [
     "ombo_gp_state_bytes", "ombo_gp_state_field", "ombo_gp_refresh", "ombo_gp_nlml_grad", "ombo_score",
     "ombo_score_host", "ombo_acquire_posterior", "ombo_pool_rows", "ombo_launch_count",
     "ombo_pack_key", "ombo_profile_enable", "ombo_profile_read",
-    "ombo_pareto_mask", "ombo_hypervolume", "ombo_cells_2d",
+    "ombo_pareto_mask", "ombo_hypervolume", "ombo_cells_2d", "ombo_posterior_joint_samples",
 ]
 
 
@@ -110,6 +110,8 @@ def lib():
                                    C.c_void_p]
     L.ombo_cells_2d.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                 C.c_void_p, C.c_void_p]
+    L.ombo_posterior_joint_samples.argtypes = [C.c_void_p, C.POINTER(Gp), C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                               C.c_double, C.c_void_p, C.c_void_p]
     L.ombo_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.ombo_profile_read.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.ombo_launch_count.argtypes = [C.c_void_p, C.c_int]

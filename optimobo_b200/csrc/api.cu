@@ -371,6 +371,17 @@ int ombo_cells_2d(ombo_ctx *ctx, const double *PF, int p, const double *ideal, c
   return ombo_cells_2d_impl(ctx, PF, p, ideal, maxp, cells, (cudaStream_t)stream);
 }
 
+int ombo_posterior_joint_samples(ombo_ctx *ctx, const ombo_gp *gp, const double *Xc, int m, const double *Z,
+                                 int n_samples, double diag_add, double *out, void *stream) {
+  OMBO_CHECK(ctx && gp && gp->state && Xc && Z && out, "joint_samples: NULL argument");
+  OMBO_CHECK(m >= 1 && m <= 16384, "joint_samples: 1 <= m <= 16384 (got %d)", m);
+  OMBO_CHECK(n_samples >= 1 && n_samples <= 4096, "joint_samples: 1 <= n_samples <= 4096 (got %d)", n_samples);
+  OMBO_CHECK(gp->n >= 1 && gp->d >= 1 && gp->d <= OMBO_MAX_DIM, "joint_samples: bad GP shape n=%d d=%d", gp->n, gp->d);
+  OMBO_CHECK(diag_add >= 0.0, "joint_samples: diag_add must be >= 0");
+  OMBO_CUDA(cudaSetDevice(ctx->device));
+  return ombo_joint_samples_impl(ctx, *gp, Xc, m, Z, n_samples, diag_add, out, (cudaStream_t)stream);
+}
+
 int ombo_profile_enable(ombo_ctx *ctx, int enable) {
   OMBO_CHECK(ctx != nullptr, "profile_enable: NULL ctx");
   OMBO_CUDA(cudaSetDevice(ctx->device));

@@ -302,6 +302,32 @@ __global__ void k_finalize(double *__restrict__ Linv, int n, int n_pad, double s
 }
 
 // ------------------------------------------------------------------------------------------
+// In-place blocked Cholesky of the lower triangle of an (np x np, np % 64 == 0) FP64 matrix; dinv receives the
+// inverted 64x64 diagonal blocks, *status the first non-positive pivot (+1) or 0.  Used by the refresh below and
+// by posterior_joint.cu (posterior covariance of a candidate set).  The status word is left on the device.
+int ombo_potrf_lower_impl(ombo_ctx *ctx, double *L, int np, int n, double *dinv, int *status, cudaStream_t s) {
+  const int nb = np / NB;
+  const size_t sm2 = (size_t)2 * NB * LDS * sizeof(double);
+  static bool attr_set = false;
+  if (!attr_set) {
+    OMBO_CUDA(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+    OMBO_CUDA(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+    attr_set = true;
+  }
+  for (int kb = 0; kb < nb; ++kb) {
+    k_potrf_diag<<<1, 64, 0, s>>>(L, np, kb, n, dinv, status);
+    ctx->launches += 1;
+    int rem = nb - kb - 1;
+    if (rem > 0) {
+      k_trsm_panel<<<rem, 256, sm2, s>>>(L, np, kb, dinv);
+      k_syrk_update<<<dim3(rem, rem), 256, sm2, s>>>(L, np, kb);
+      ctx->launches += 2;
+    }
+  }
+  OMBO_CUDA(cudaGetLastError());
+  return OMBO_OK;
+}
+
 int ombo_refresh_impl(ombo_ctx *ctx, const ombo_gp_spec *sp, void *state, cudaStream_t s) {
   const GpLayout lay = gp_layout(sp->n, sp->d);
   const int n = sp->n, d = sp->d, np = lay.n_pad, nb = np / NB;
@@ -325,23 +351,8 @@ int ombo_refresh_impl(ombo_ctx *ctx, const ombo_gp_spec *sp, void *state, cudaSt
   dim3 tb(16, 16), gb(np / 16, np / 16);
   k_build_K<<<gb, tb, 0, s>>>(xs, n, d, np, sp->sigma_f2, sp->sigma_n2 + sp->jitter, sp->kernel, L);
   ctx->launches += 2;
-  const size_t sm2 = (size_t)2 * NB * LDS * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    OMBO_CUDA(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-    OMBO_CUDA(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-    attr_set = true;
-  }
-  for (int kb = 0; kb < nb; ++kb) {
-    k_potrf_diag<<<1, 64, 0, s>>>(L, np, kb, n, dinv, status);
-    ctx->launches += 1;
-    int rem = nb - kb - 1;
-    if (rem > 0) {
-      k_trsm_panel<<<rem, 256, sm2, s>>>(L, np, kb, dinv);
-      k_syrk_update<<<dim3(rem, rem), 256, sm2, s>>>(L, np, kb);
-      ctx->launches += 2;
-    }
-  }
+  int rc = ombo_potrf_lower_impl(ctx, L, np, n, dinv, status, s);
+  if (rc) return rc;
   k_trtri_cols<<<np / TC, 256, 0, s>>>(L, np, nb, dinv, Linv);
   // alpha = Linv^T (Linv y); ypad currently lives in alpha
   k_trmv_lower<<<(np + 7) / 8, 256, 0, s>>>(Linv, np, np, alpha, tmp);

@@ -130,6 +130,41 @@ class GPModel:
             return mu, np.sqrt(np.maximum(var, 0.0))
         return mu.reshape(-1, 1), var.reshape(-1, 1)
 
+    def posterior_samples(self, X, size=10, rng=None, jitter=None, max_jitter_tries=6):
+        """Joint posterior samples at X (m,d) -> (m, 1, size), GPy's `posterior_samples` shape
+        (turbo.py:116).  out = mu + chol(Sigma + (noise + jitter) I) Z with Z ~ N(0, I) drawn from `rng`
+        on the host; covariance, Cholesky and the product run on the device in FP64
+        (`ombo_posterior_joint_samples`).  The jitter starts at 1e-8 sigma_f^2 and is raised x10 while the
+        posterior covariance is not numerically positive definite (GPy's jitchol policy)."""
+        Z = (np.random.default_rng() if rng is None else rng).standard_normal((len(np.atleast_2d(X)), int(size)))
+        return self.posterior_samples_from(X, Z, jitter, max_jitter_tries)
+
+    posterior_samples_f = posterior_samples      # noise is fixed to 0 on this path (optimisers.py:229)
+
+    def posterior_samples_from(self, X, Z, jitter=None, max_jitter_tries=6):
+        """As `posterior_samples`, with the standard-normal draws Z (m, size) supplied (parity tests)."""
+        Xd = torch.as_tensor(np.ascontiguousarray(np.atleast_2d(np.asarray(X, dtype=np.float64)))).to(self.device)
+        Zd = torch.as_tensor(np.ascontiguousarray(np.asarray(Z, dtype=np.float64))).to(self.device)
+        m, S = Zd.shape
+        if Xd.shape != (m, self.d):
+            raise ValueError(f"X must be ({m}, {self.d}), got {tuple(Xd.shape)}")
+        out = torch.empty((m, S), dtype=torch.float64, device=self.device)
+        ctx = _cabi.Context.get(self.device.index or 0)
+        g = self.c_struct()
+        jit = 1e-8 * self.variance if jitter is None else float(jitter)
+        for attempt in range(max_jitter_tries + 1):
+            with torch.cuda.device(self.device):
+                rc = _cabi.lib().ombo_posterior_joint_samples(
+                    ctx.handle, C.byref(g), C.c_void_p(Xd.data_ptr()), m, C.c_void_p(Zd.data_ptr()), S,
+                    self.noise + jit, C.c_void_p(out.data_ptr()), current_stream_ptr(self.device))
+            if rc == _cabi.ERR_NOT_PD and attempt < max_jitter_tries:
+                jit = max(jit, 1e-10 * self.variance) * 10.0
+                continue
+            _cabi.check(rc)
+            break
+        self.sample_jitter = jit
+        return out.cpu().numpy().reshape(m, 1, S)
+
     @classmethod
     def from_gpy(cls, gpy_model, device=None):
         """Adopts the hyper-parameters of a fitted GPy GPRegression (reference models)."""

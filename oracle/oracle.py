@@ -97,6 +97,28 @@ def gp_posterior(state, Xnew, chunk=8192, var_floor=1e-15):
     return mu, var
 
 
+def gp_posterior_joint(state, Xnew):
+    """Joint posterior (mu (m,), Sigma (m,m)) -- GPy posterior.py::_raw_predict(full_cov=True):
+    Sigma = Kxx - tmp^T tmp with tmp = dtrtrs(LW, Kx); the call site is GP.posterior_samples
+    (turbo.py:116)."""
+    Xnew = np.atleast_2d(np.asarray(Xnew, float))
+    Kx = k_of_r(scaled_dist(state["X"], Xnew, state["ell"], state["form"]), state["sigma_f2"], state["kernel"])
+    mu = Kx.T @ state["alpha"]
+    tmp = sla.solve_triangular(state["L"], Kx, lower=True, check_finite=False)
+    Kxx = k_of_r(scaled_dist(Xnew, Xnew, state["ell"], state["form"]), state["sigma_f2"], state["kernel"])
+    np.fill_diagonal(Kxx, state["sigma_f2"])
+    return mu, Kxx - tmp.T @ tmp
+
+
+def posterior_samples(state, Xnew, Z, diag_add):
+    """mu + chol(Sigma + diag_add I) Z: the Cholesky form of a joint draw (GPy draws through
+    np.random.multivariate_normal; the two agree in distribution, and the Cholesky form is what a
+    given Z pins down)."""
+    mu, S = gp_posterior_joint(state, Xnew)
+    Lc = np.linalg.cholesky(S + diag_add * np.eye(len(mu)))
+    return mu[:, None] + Lc @ np.asarray(Z, float)
+
+
 def gp_posterior_std(state, Xnew):
     """sklearn surface (util_functions.py:265): (mean (m,), std (m,)), negative
     variances zeroed (sklearn _gpr.py:480-500)."""

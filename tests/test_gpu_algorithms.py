@@ -242,3 +242,16 @@ def test_device_prep_inside_solve_changes_nothing():
                   hyperparameters=hyper, refine_rounds=0, prep_on_device=on_dev)
         emo.append(opt.solve(budget=3, n_init_samples=10))
     np.testing.assert_array_equal(emo[0].Xsample, emo[1].Xsample)
+
+
+def test_turbo_1_runs_and_improves():
+    """TuRBO-1 (turbo.py) on the device sampling path: batches of Thompson samples over the trust region."""
+    from optimobo_b200.algorithms import TuRBO_1
+    opt = TuRBO_1(ReadmeProblem(), batch_size=4, ideal_point=[0, 0], max_point=[700.0, 12.0], seed=0, max_f_eval=100)
+    assert opt.n_cand == 200 and opt.failtol == 1
+    res = opt.solve(sc.Tchebicheff([0, 0], [700.0, 12.0]), budget=45, n_init_samples=8)
+    assert res.ysample.shape[0] >= 45 and res.ysample.shape[1] == 2 and res.Xsample.shape[0] == res.ysample.shape[0]
+    assert np.all(res.Xsample >= -2 - 1e-12) and np.all(res.Xsample <= 2 + 1e-12)
+    agg = np.maximum(0.5 * res.ysample[:, 0] / 700.0, 0.5 * res.ysample[:, 1] / 12.0)
+    assert agg[8:].min() <= agg[:8].min()                 # the model-guided batches find a better point than the design
+    assert len(res.pf_approx) >= 1 and len(res.hypervolume_convergence) >= 1

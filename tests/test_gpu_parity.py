@@ -580,3 +580,55 @@ def test_device_cells_match_host_oracle_and_feed_hv_poi(n):
     a_dev, _, _ = ob.acquire_from_posterior(ob.spec_hv_poi(cells.cpu().numpy()), mu, var, device=DEV)
     a_ora = O.hv_poi_batched(mu.T, var.T, O.decompose_into_cells_2d(pf, ideal, maxp))
     np.testing.assert_allclose(a_dev.cpu().numpy(), a_ora, rtol=1e-9, atol=1e-300)
+
+
+# ------------------------------------------------------------------------------------------
+# joint posterior samples (the device side of TuRBO's Thompson sampling)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,m,S,kernel", [(30, 2, 200, 4, "matern52"), (100, 5, 1000, 3, "matern52"),
+                                            (64, 3, 129, 1, "rbf"), (200, 10, 1000, 10, "matern52"),
+                                            (257, 4, 63, 5, "matern52")])
+def test_joint_posterior_samples_vs_oracle(n, d, m, S, kernel):
+    """out = mu + chol(Sigma + diag_add I) Z against the numpy/LAPACK restatement on the same Z.  The
+    jitter keeps the m x m covariance comfortably positive definite so that both Cholesky factors
+    are well conditioned (rtol 1e-6 of the sample scale)."""
+    X, Y, ells, sf2 = make_problem(n, d)
+    noise = 1e-4 if kernel == "rbf" else 0.0
+    gp = ob.GPModel(X, Y[:, 0], ells[0], sf2[0], noise=noise, kernel=kernel, device=DEV)
+    st = O.gp_fit_state(X, Y[:, 0], ells[0], sf2[0], sigma_n2=noise,
+                        kernel=O.KERNEL_RBF if kernel == "rbf" else O.KERNEL_MATERN52, form="direct")
+    rng = np.random.default_rng(n + m)
+    Xc = rng.random((m, d))
+    Z = rng.standard_normal((m, S))
+    jitter = 1e-6 * sf2[0]
+    got = gp.posterior_samples_from(Xc, Z, jitter=jitter)
+    assert got.shape == (m, 1, S) and gp.sample_jitter == jitter
+    want = O.posterior_samples(st, Xc, Z, noise + jitter)
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(got[:, 0, :], want, rtol=1e-6, atol=2e-6 * scale)
+    # Z = 0 returns the posterior mean of the scoring path
+    mu = gp.posterior_samples_from(Xc, np.zeros((m, 1)), jitter=jitter)[:, 0, 0]
+    mu_ref, _ = ob.posterior([gp], Xc)
+    np.testing.assert_allclose(mu, mu_ref[0].cpu().numpy(), rtol=1e-9, atol=1e-9 * max(1.0, np.abs(mu).max()))
+
+
+def test_joint_posterior_samples_statistics_and_jitter_retry():
+    """Distributional check (what the reference's np.random.multivariate_normal draw shares with the
+    Cholesky draw): sample mean -> mu, sample variance -> diag(Sigma); and duplicate candidates
+    (singular covariance) are handled by the jitchol-style retry."""
+    n, d, m, S = 60, 3, 150, 4000
+    X, Y, ells, sf2 = make_problem(n, d)
+    gp = ob.GPModel(X, Y[:, 1], ells[1], sf2[1], device=DEV)
+    st = O.gp_fit_state(X, Y[:, 1], ells[1], sf2[1], form="direct")
+    Xc = np.random.default_rng(1).random((m, d))
+    smp = gp.posterior_samples(Xc, size=S, rng=np.random.default_rng(2))[:, 0, :]
+    mu, Sig = O.gp_posterior_joint(st, Xc)
+    sd = np.sqrt(np.diag(Sig))
+    assert np.abs(smp.mean(1) - mu).max() < 6 * sd.max() / np.sqrt(S)
+    np.testing.assert_allclose(smp.std(1), sd, rtol=0.1, atol=1e-3)
+    Xdup = np.vstack((Xc[:40], Xc[:40]))
+    out = gp.posterior_samples(Xdup, size=3, rng=np.random.default_rng(3), jitter=0.0)
+    assert np.all(np.isfinite(out)) and gp.sample_jitter > 0
+    np.testing.assert_allclose(out[:40], out[40:], atol=1e-2 * np.sqrt(sf2[1]))
+    with pytest.raises(ValueError):
+        gp.posterior_samples_from(Xc[:, :2], np.zeros((m, 1)))
