@@ -134,3 +134,103 @@ class TuRBO_1(PoolOptimiserBase):
         mask = self._pareto_members(self.ysample)
         return result.Res(self.ysample[mask], self.Xsample[mask], self.ysample, self.Xsample, hypervolume_convergence,
                           self.n_obj, n_init_samples)
+
+
+class TuRBO_M(TuRBO_1):
+    """TuRBO-m (turbo.py:309-573): `n_trust_regions` local models, every batch takes the best Thompson
+    samples across all regions.  Same device path per region as TuRBO_1."""
+
+    def __init__(self, test_problem, ideal_point, max_point, batch_size, n_trust_regions, **kw):
+        self.n_trust_regions = int(n_trust_regions)
+        super().__init__(test_problem, batch_size, ideal_point, max_point, **kw)
+        self.succtol = 3
+        self.failtol = max(5, self.n_vars)
+        self.aggregated_samples = np.zeros((0, 1))
+        self._restart()
+
+    def _restart(self):
+        self._idx = np.zeros((0, 1), dtype=int)          # which trust region proposed which sample
+        self.failcount = np.zeros(self.n_trust_regions, dtype=int)
+        self.succcount = np.zeros(self.n_trust_regions, dtype=int)
+        self.length = self.length_init * np.ones(self.n_trust_regions)
+
+    def _adjust_length(self, fX_next, i):
+        fX_min = self.ysample[self._idx[:, 0] == i, 0].min()      # the reference's target value (turbo.py:348)
+        if fX_next.min() < fX_min - 1e-3 * math.fabs(fX_min):
+            self.succcount[i] += 1
+            self.failcount[i] = 0
+        else:
+            self.succcount[i] = 0
+            self.failcount[i] += len(fX_next)
+        if self.succcount[i] == self.succtol:
+            self.length[i] = min(2.0 * self.length[i], self.length_max)
+            self.succcount[i] = 0
+        elif self.failcount[i] >= self.failtol:
+            self.length[i] /= 2.0
+            self.failcount[i] = 0
+
+    def _select_candidates(self, X_cand, y_cand):
+        X_next = np.zeros((self.batch_size, self.n_vars))
+        idx_next = np.zeros((self.batch_size, 1), dtype=int)
+        for k in range(self.batch_size):
+            i, j = np.unravel_index(np.argmin(y_cand[:, :, k]), (self.n_trust_regions, self.n_cand))
+            X_next[k, :] = X_cand[i, j, :]
+            idx_next[k, 0] = i
+            y_cand[i, j, :] = np.inf
+        return X_next, idx_next
+
+    def _init_region(self, i, aggregation_func, weights, n_init_samples):
+        Xsample, ysample = self._initial_design(n_init_samples)
+        aggregated = np.asarray([aggregation_func(y, weights) for y in ysample]).reshape(-1, 1)
+        self.n_evals += n_init_samples
+        self._idx = np.vstack((self._idx, i * np.ones((n_init_samples, 1), dtype=int)))
+        self.Xsample = np.vstack((self.Xsample, Xsample))
+        self.ysample = np.vstack((self.ysample, ysample))
+        self.aggregated_samples = np.vstack((self.aggregated_samples, aggregated))
+
+    def solve(self, aggregation_func, budget, n_init_samples):
+        self.budget = budget
+        assert self.n_trust_regions > 1 and isinstance(budget, int)
+        assert budget > self.n_trust_regions * n_init_samples, "Not enough trust regions to do initial evaluations"
+        assert budget > self.batch_size, "Not enough evaluations to do a single batch"
+        problem = self.test_problem
+        hypervolume_convergence = []
+        uniform = np.full(self.n_obj, 1.0 / self.n_obj)
+        for i in range(self.n_trust_regions):
+            self._init_region(i, aggregation_func, self.get_random_weight(), n_init_samples)
+        self._update_bounds(self.ysample, aggregation_func)
+        while self.n_evals < self.budget:
+            self._update_bounds(self.ysample, aggregation_func)
+            hypervolume_convergence.append(self._hypervolume(self.ysample))
+            X_cand = np.zeros((self.n_trust_regions, self.n_cand, self.n_vars))
+            y_cand = np.inf * np.ones((self.n_trust_regions, self.n_cand, self.batch_size))
+            for i in range(self.n_trust_regions):
+                idx = np.where(self._idx == i)[0]
+                Xn = self.normalise(self.Xsample[idx, :])
+                aggre = self.aggregated_samples[idx, :]
+                GP = self._fit_model(Xn, aggre[:, 0])
+                X_cand[i], y_i = self.create_candidates(Xn, aggre, GP, length=self.length[i])
+                y_cand[i] = y_i.reshape(self.n_cand, self.batch_size)
+            X_next, idx_next = self._select_candidates(X_cand, y_cand)
+            X_next = self.denormalise(X_next)
+            ref_dir = self.get_random_weight()
+            y_next = np.asarray([self._objective_function(problem, x) for x in X_next])
+            aggregated_next = np.asarray([aggregation_func(y, ref_dir) for y in y_next]).reshape(-1)
+            for i in range(self.n_trust_regions):
+                idx_i = np.where(idx_next == i)[0]
+                if len(idx_i) > 0:
+                    self._adjust_length(aggregated_next[idx_i], i)
+            self.n_evals += self.batch_size
+            self.Xsample = np.vstack((self.Xsample, X_next))
+            self.ysample = np.vstack((self.ysample, y_next))
+            self.aggregated_samples = np.vstack((self.aggregated_samples, aggregated_next.reshape(-1, 1)))
+            self._idx = np.vstack((self._idx, idx_next))
+            for i in range(self.n_trust_regions):
+                if self.length[i] < self.length_min:              # converged: restart this region
+                    self._idx[self._idx[:, 0] == i, 0] = -1
+                    self.length[i] = self.length_init
+                    self.succcount[i] = self.failcount[i] = 0
+                    self._init_region(i, aggregation_func, uniform, n_init_samples)
+        mask = self._pareto_members(self.ysample)
+        return result.Res(self.ysample[mask], self.Xsample[mask], self.ysample, self.Xsample, hypervolume_convergence,
+                          self.n_obj, n_init_samples)

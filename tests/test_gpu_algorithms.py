@@ -255,3 +255,12 @@ def test_turbo_1_runs_and_improves():
     agg = np.maximum(0.5 * res.ysample[:, 0] / 700.0, 0.5 * res.ysample[:, 1] / 12.0)
     assert agg[8:].min() <= agg[:8].min()                 # the model-guided batches find a better point than the design
     assert len(res.pf_approx) >= 1 and len(res.hypervolume_convergence) >= 1
+
+
+def test_turbo_m_runs():
+    from optimobo_b200.algorithms import TuRBO_M
+    opt = TuRBO_M(ReadmeProblem(), [0, 0], [700.0, 12.0], batch_size=3, n_trust_regions=2, seed=1, max_f_eval=60)
+    res = opt.solve(sc.Tchebicheff([0, 0], [700.0, 12.0]), budget=30, n_init_samples=6)
+    assert res.ysample.shape[0] >= 30 and res.Xsample.shape == (res.ysample.shape[0], 2)
+    assert set(np.unique(opt._idx)) <= {-1, 0, 1} and len(opt._idx) == len(res.ysample)
+    assert np.all(np.isfinite(res.ysample)) and len(res.pf_approx) >= 1
