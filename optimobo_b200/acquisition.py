@@ -17,6 +17,7 @@ Everything goes through the C ABI (`_cabi`); there is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -252,6 +253,12 @@ def score(models, spec, pool, precision="fp64", want_posterior=False, want_acq=F
             raise ValueError("all models must live on the same device")
     if pool.X is not None and pool.X.device != dev:
         raise ValueError("pool and models are on different devices")
+    if precision == "fast":
+        worst = max(mdl.conditioning for mdl in models)
+        if worst > GPModel.FAST_MODE_CONDITIONING_LIMIT:
+            warnings.warn(f"fast precision on an ill-conditioned GP (conditioning proxy {worst:.1e} > "
+                          f"{GPModel.FAST_MODE_CONDITIONING_LIMIT:.0e}): sigma may be off by more than 1e-3 sigma_f; "
+                          "use precision='fp64' or 'auto'", RuntimeWarning, stacklevel=2)
     G = len(models)
     gps = (_cabi.Gp * G)(*[m.c_struct(var_floor) for m in models])
     p = pool.c_struct()

@@ -113,7 +113,12 @@ class PoolOptimiserBase:
         # training points (DESIGN.md "fast mode validity")
         n = max(m.n for m in models)
         d = models[0].d
-        return "fast" if (_cabi.fast_path_available() and n > 256 and d <= 24) else "fp64"
+        if not (_cabi.fast_path_available() and n > 256 and d <= 24):
+            return "fp64"
+        # ... and large but ill-conditioned ones (many points per length-scale in few dimensions): the bf16x3
+        # split then loses absolute accuracy on sigma (GPModel.conditioning, scripts/cond_study.py)
+        from ..gp import GPModel
+        return "fast" if max(m.conditioning for m in models) <= GPModel.FAST_MODE_CONDITIONING_LIMIT else "fp64"
 
     # ---- the seam: pool scoring + arg-max instead of DE / EA ---------------------------------
     def _propose(self, models, spec):

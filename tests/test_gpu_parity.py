@@ -632,3 +632,29 @@ def test_joint_posterior_samples_statistics_and_jitter_retry():
     np.testing.assert_allclose(out[:40], out[40:], atol=1e-2 * np.sqrt(sf2[1]))
     with pytest.raises(ValueError):
         gp.posterior_samples_from(Xc[:, :2], np.zeros((m, 1)))
+
+
+def test_conditioning_proxy_guards_the_fast_mode():
+    """GPModel.conditioning = (max L_ii / min L_ii)^2; the optimisers' precision="auto" falls back to FP64
+    on large but ill-conditioned GPs, an explicit precision="fast" warns."""
+    import warnings
+    from optimobo_b200.algorithms.base import PoolOptimiserBase
+    from optimobo_b200.problem import Problem
+    rng = np.random.default_rng(0)
+    good_X, bad_X = rng.random((400, 10)), rng.random((400, 2))
+    y = np.sin(3 * good_X.sum(1))
+    good = ob.GPModel(good_X, y, 0.7 * np.ones(10), 1.5, device=DEV)
+    bad = ob.GPModel(bad_X, y, 0.3 * np.ones(2), 1.5, device=DEV)
+    for gp, X, ell in ((good, good_X, 0.7), (bad, bad_X, 0.3)):
+        dg = np.diag(O.gp_fit_state(X, y, ell * np.ones(X.shape[1]), 1.5, form="direct")["L"])
+        assert gp.conditioning == pytest.approx((dg.max() / dg.min()) ** 2, rel=1e-6)
+    assert good.conditioning < 1e3 < bad.conditioning
+    base = PoolOptimiserBase(Problem(n_var=10, n_obj=2, xl=np.zeros(10), xu=np.ones(10)), device=DEV)
+    if _cabi.fast_path_available():
+        assert base._precision_for([good]) == "fast" and base._precision_for([bad]) == "fp64"
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            ob.posterior([good], good_X[:10], precision="fast")
+            assert not [x for x in w if issubclass(x.category, RuntimeWarning)]
+            ob.posterior([bad], bad_X[:10], precision="fast")
+            assert [x for x in w if issubclass(x.category, RuntimeWarning)]
