@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -71,7 +72,7 @@ int ombo_ws_reserve(void **p, size_t *cur, size_t want);
 struct GpLayout {
   int n, d, n_pad;
   size_t off_L, off_Linv, off_alpha, off_xs, off_status, off_dinv, off_tmp, off_inv_ell;
-  size_t off_bhi, off_blo, off_xs32, off_alpha32, off_center, off_b2;
+  size_t off_bhi, off_blo, off_xs32, off_alpha32, off_center, off_b2, off_bscale;
   size_t bytes;
 };
 
@@ -96,6 +97,7 @@ static inline GpLayout gp_layout(int n, int d) {
   L.off_alpha32 = take(np * 4);
   L.off_center = take((size_t)OMBO_MAX_DIM * 8);
   L.off_b2 = take(np * 4);
+  L.off_bscale = take(32);                // [0] max |sigma_f2 L^-1| (bits), [1] power-of-two scale s of the fp16 planes, [2] 1/s^2
   L.bytes = off;
   return L;
 }
@@ -103,12 +105,14 @@ static inline GpLayout gp_layout(int n, int d) {
 // device-side view of one GP used by the scoring kernels
 struct GpDev {
   int n, n_pad, d, kernel;
+  int flags;              // ombo_gp.reserved: bit 0 = OMBO_GP_DIRECT_DISTANCES (fast mode)
   double sigma_f2, sigma_n2, var_floor;
   const double *xs;       // (d, n_pad) scaled
   const double *ell;      // (d) length-scales
   const double *Linv;     // (n_pad, n_pad)
   const double *alpha;    // (n_pad)
-  const __nv_bfloat16 *bhi, *blo;
+  const __half *bhi, *blo;               // fp16 hi / lo planes of s * sigma_f2 * L^-1
+  const double *bscale;                  // [1] = s, [2] = 1 / s^2 (power of two: exact)
   const float *xs32, *alpha32, *b2_32;   // fast path: centred scaled inputs, sigma_f2*alpha, |xs32_i|^2
   const double *center;                  // (d) per-dimension mean of the training inputs
 };
@@ -117,14 +121,15 @@ static inline GpDev gp_dev_view(const ombo_gp &g) {
   GpLayout L = gp_layout(g.n, g.d);
   const char *b = (const char *)g.state;
   GpDev v;
-  v.n = g.n; v.n_pad = L.n_pad; v.d = g.d; v.kernel = g.kernel;
+  v.n = g.n; v.n_pad = L.n_pad; v.d = g.d; v.kernel = g.kernel; v.flags = g.reserved;
   v.sigma_f2 = g.sigma_f2; v.sigma_n2 = g.sigma_n2; v.var_floor = g.var_floor;
   v.xs = (const double *)(b + L.off_xs);
   v.ell = (const double *)(b + L.off_inv_ell);
   v.Linv = (const double *)(b + L.off_Linv);
   v.alpha = (const double *)(b + L.off_alpha);
-  v.bhi = (const __nv_bfloat16 *)(b + L.off_bhi);
-  v.blo = (const __nv_bfloat16 *)(b + L.off_blo);
+  v.bhi = (const __half *)(b + L.off_bhi);
+  v.blo = (const __half *)(b + L.off_blo);
+  v.bscale = (const double *)(b + L.off_bscale);
   v.xs32 = (const float *)(b + L.off_xs32);
   v.alpha32 = (const float *)(b + L.off_alpha32);
   v.b2_32 = (const float *)(b + L.off_b2);

@@ -282,22 +282,39 @@ __global__ void k_trmv_lower_t(const double *__restrict__ M, int ld, int n_pad, 
   }
 }
 
+// max |L^-1| over the valid lower triangle (bit pattern of a non-negative double orders like the value)
+__global__ void k_absmax_lower(const double *__restrict__ Linv, int n, int n_pad, unsigned long long *__restrict__ out) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (e < (size_t)n_pad * n_pad) {
+    const int j = (int)(e / n_pad), i = (int)(e % n_pad);
+    if (j < n && i <= j) v = fabs(Linv[e]);
+  }
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(v));
+}
+
 // zero the padding of L^-1 and emit the fast-path operands:
-//   B = sigma_f2 * L^-1 split into bf16 hi + lo planes, alpha32 = sigma_f2 * alpha
+//   B = s * sigma_f2 * L^-1 split into fp16 hi + lo planes (s = the power of two that brings max |B| to
+//   [8192, 16384): fp16 has 11 significant bits against bf16's 8, so the 3-product split carries 22 bits,
+//   and the scale keeps ill-conditioned factors inside its range), alpha32 = sigma_f2 * alpha
 __global__ void k_finalize(double *__restrict__ Linv, int n, int n_pad, double sf2,
-                           __nv_bfloat16 *__restrict__ bhi, __nv_bfloat16 *__restrict__ blo,
+                           __half *__restrict__ bhi, __half *__restrict__ blo, double *__restrict__ bscale,
                            const double *__restrict__ alpha, float *__restrict__ alpha32) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)n_pad * n_pad;
   if (e >= total) return;
+  const double mx = bscale[0] * sf2;                       // bscale[0] holds the double written by k_absmax_lower
+  const double sc = mx > 0.0 ? exp2(floor(log2(16384.0 / mx))) : 1.0;
+  if (e == 0) { bscale[1] = sc; bscale[2] = 1.0 / (sc * sc); }
   int j = (int)(e / n_pad), i = (int)(e % n_pad);
   double v = Linv[e];
   if (j >= n || i >= n || i > j) { v = 0.0; Linv[e] = 0.0; }
-  float f = (float)(v * sf2);
-  __nv_bfloat16 h = __float2bfloat16_rn(f);
-  float rem = (float)(v * sf2 - (double)__bfloat162float(h));
+  const double t = v * sf2 * sc;
+  const __half h = __float2half_rn((float)t);
+  const float rem = (float)(t - (double)__half2float(h));
   bhi[e] = h;
-  blo[e] = __float2bfloat16_rn(rem);
+  blo[e] = __float2half_rn(rem);
   if (e < (size_t)n_pad) alpha32[e] = (float)(alpha[e] * sf2);
 }
 
@@ -337,7 +354,8 @@ int ombo_refresh_impl(ombo_ctx *ctx, const ombo_gp_spec *sp, void *state, cudaSt
   int *status = (int *)(b + lay.off_status);
   double *dinv = (double *)(b + lay.off_dinv), *tmp = (double *)(b + lay.off_tmp);
   double *ell_dev = (double *)(b + lay.off_inv_ell);
-  __nv_bfloat16 *bhi = (__nv_bfloat16 *)(b + lay.off_bhi), *blo = (__nv_bfloat16 *)(b + lay.off_blo);
+  __half *bhi = (__half *)(b + lay.off_bhi), *blo = (__half *)(b + lay.off_blo);
+  double *bscale = (double *)(b + lay.off_bscale);
   float *xs32 = (float *)(b + lay.off_xs32), *alpha32 = (float *)(b + lay.off_alpha32);
   float *b2 = (float *)(b + lay.off_b2);
   double *center = (double *)(b + lay.off_center);
@@ -358,8 +376,10 @@ int ombo_refresh_impl(ombo_ctx *ctx, const ombo_gp_spec *sp, void *state, cudaSt
   k_trmv_lower<<<(np + 7) / 8, 256, 0, s>>>(Linv, np, np, alpha, tmp);
   k_trmv_lower_t<<<(np + 31) / 32, dim3(32, 8), 0, s>>>(Linv, np, np, tmp, alpha);
   size_t total = (size_t)np * np;
-  k_finalize<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Linv, n, np, sp->sigma_f2, bhi, blo, alpha, alpha32);
-  ctx->launches += 4;
+  OMBO_CUDA(cudaMemsetAsync(bscale, 0, 32, s));
+  k_absmax_lower<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Linv, n, np, (unsigned long long *)bscale);
+  k_finalize<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Linv, n, np, sp->sigma_f2, bhi, blo, bscale, alpha, alpha32);
+  ctx->launches += 5;
   OMBO_CUDA(cudaGetLastError());
   int hstatus[4] = {0, 0, 0, 0};
   OMBO_CUDA(cudaMemcpyAsync(hstatus, status, 16, cudaMemcpyDeviceToHost, s));

@@ -52,7 +52,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
   constexpr int CW = (PAIR || WIDE) ? 256 : 128; // accumulator chunk width = widest UMMA N
   constexpr int NSLOT = 512 / CW;                // TMEM accumulator slots
   constexpr int KSH = (PAIR || WIDE) ? 2 : 1;    // chunk c needs K-blocks kb < (c + 1) << KSH
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CW >> 3) << 17) |
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(CW >> 3) << 17) |
                              ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = prm.gp.d, np = prm.gp.n_pad;
@@ -301,7 +301,8 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
       }
       const long long cg = tile * FM + row;
       if (cg < prm.m) {
-        double v = prm.gp.sigma_f2 - ss;       // V = k' (sigma_f2 L^-1)^T = L^-1 k*, so ss = ||L^-1 k*||^2
+        // V = k' (s sigma_f2 L^-1)^T = s L^-1 k*, so ss = s^2 ||L^-1 k*||^2 (s: power-of-two scale of the fp16 planes)
+        double v = prm.gp.sigma_f2 - ss * prm.gp.bscale[2];
         prm.var_out[cg] = fmax(v, prm.gp.var_floor) + prm.gp.sigma_n2;
       }
     }
@@ -424,29 +425,52 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
               }
             }
             float2 r2[R][4];
-            {
-              const float4 n0 = *(const float4 *)(xs + (DP + 1) * FK);      // |b_i|^2
-              const float4 n1 = *(const float4 *)(xs + (DP + 1) * FK + 4);
+            if (prm.gp.flags & OMBO_GP_DIRECT_DISTANCES) {
+              // direct differences: (b_j - a_j)^2 summed, no |a|^2 + |b|^2 - 2 a.b cancellation (ill-conditioned GPs)
 #pragma unroll
-              for (int rr = 0; rr < R; ++rr) {
-                const float2 aa = make_float2(a2[rr], a2[rr]);
-                r2[rr][0] = __fadd2_rn(aa, make_float2(n0.x, n0.y));
-                r2[rr][1] = __fadd2_rn(aa, make_float2(n0.z, n0.w));
-                r2[rr][2] = __fadd2_rn(aa, make_float2(n1.x, n1.y));
-                r2[rr][3] = __fadd2_rn(aa, make_float2(n1.z, n1.w));
+              for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) r2[rr][e] = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int j = 0; j < DP; ++j) {
+                const float4 t0 = *(const float4 *)(xs + j * FK);
+                const float4 t1 = *(const float4 *)(xs + j * FK + 4);
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                  const float2 xx = make_float2(x[rr][j], x[rr][j]), hh = make_float2(0.5f, 0.5f);   // x = -2 a_j
+                  const float2 d0 = __ffma2_rn(xx, hh, make_float2(t0.x, t0.y)), d1 = __ffma2_rn(xx, hh, make_float2(t0.z, t0.w));
+                  const float2 d2 = __ffma2_rn(xx, hh, make_float2(t1.x, t1.y)), d3 = __ffma2_rn(xx, hh, make_float2(t1.z, t1.w));
+                  r2[rr][0] = __ffma2_rn(d0, d0, r2[rr][0]);
+                  r2[rr][1] = __ffma2_rn(d1, d1, r2[rr][1]);
+                  r2[rr][2] = __ffma2_rn(d2, d2, r2[rr][2]);
+                  r2[rr][3] = __ffma2_rn(d3, d3, r2[rr][3]);
+                }
               }
-            }
+            } else {
+              {
+                const float4 n0 = *(const float4 *)(xs + (DP + 1) * FK);      // |b_i|^2
+                const float4 n1 = *(const float4 *)(xs + (DP + 1) * FK + 4);
 #pragma unroll
-            for (int j = 0; j < DP; ++j) {
-              const float4 t0 = *(const float4 *)(xs + j * FK);
-              const float4 t1 = *(const float4 *)(xs + j * FK + 4);
+                for (int rr = 0; rr < R; ++rr) {
+                  const float2 aa = make_float2(a2[rr], a2[rr]);
+                  r2[rr][0] = __fadd2_rn(aa, make_float2(n0.x, n0.y));
+                  r2[rr][1] = __fadd2_rn(aa, make_float2(n0.z, n0.w));
+                  r2[rr][2] = __fadd2_rn(aa, make_float2(n1.x, n1.y));
+                  r2[rr][3] = __fadd2_rn(aa, make_float2(n1.z, n1.w));
+                }
+              }
 #pragma unroll
-              for (int rr = 0; rr < R; ++rr) {
-                const float2 xx = make_float2(x[rr][j], x[rr][j]);            // -2 a_j
-                r2[rr][0] = __ffma2_rn(xx, make_float2(t0.x, t0.y), r2[rr][0]);
-                r2[rr][1] = __ffma2_rn(xx, make_float2(t0.z, t0.w), r2[rr][1]);
-                r2[rr][2] = __ffma2_rn(xx, make_float2(t1.x, t1.y), r2[rr][2]);
-                r2[rr][3] = __ffma2_rn(xx, make_float2(t1.z, t1.w), r2[rr][3]);
+              for (int j = 0; j < DP; ++j) {
+                const float4 t0 = *(const float4 *)(xs + j * FK);
+                const float4 t1 = *(const float4 *)(xs + j * FK + 4);
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                  const float2 xx = make_float2(x[rr][j], x[rr][j]);            // -2 a_j
+                  r2[rr][0] = __ffma2_rn(xx, make_float2(t0.x, t0.y), r2[rr][0]);
+                  r2[rr][1] = __ffma2_rn(xx, make_float2(t0.z, t0.w), r2[rr][1]);
+                  r2[rr][2] = __ffma2_rn(xx, make_float2(t1.x, t1.y), r2[rr][2]);
+                  r2[rr][3] = __ffma2_rn(xx, make_float2(t1.z, t1.w), r2[rr][3]);
+                }
               }
             }
             const float4 al0 = *(const float4 *)(xs + DP * FK);
@@ -489,10 +513,10 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
               uint32_t hi[4], lo[4];
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                __nv_bfloat162 h = __float22bfloat162_rn(kv[e]);
+                __half2 h = __float22half2_rn(kv[e]);
                 const uint32_t hb = *reinterpret_cast<uint32_t *>(&h);
-                const float2 hf = make_float2(__uint_as_float(hb << 16), __uint_as_float(hb & 0xffff0000u));
-                __nv_bfloat162 l = __float22bfloat162_rn(__ffma2_rn(hf, make_float2(-1.0f, -1.0f), kv[e]));   // k' - hi, exact
+                const float2 hf = __half22float2(h);
+                __half2 l = __float22half2_rn(__ffma2_rn(hf, make_float2(-1.0f, -1.0f), kv[e]));   // k' - hi, exact
                 hi[e] = hb;
                 lo[e] = *reinterpret_cast<uint32_t *>(&l);
               }
@@ -574,7 +598,7 @@ static int make_b_map(CUtensorMap *map, const void *base, int n_pad, int box_row
   cuuint64_t strides[1] = {(cuuint64_t)n_pad * 2};
   cuuint32_t box[2] = {FK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { ombo_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return OMBO_ERR_CUDA; }
@@ -589,7 +613,7 @@ static int make_linear_map(CUtensorMap *map, const void *base, size_t rows) {
   cuuint64_t strides[1] = {128};
   cuuint32_t box[2] = {64, 256};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { ombo_set_error("cuTensorMapEncodeTiled (cache) failed (%d)", (int)r); return OMBO_ERR_CUDA; }

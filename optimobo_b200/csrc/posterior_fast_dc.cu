@@ -46,7 +46,7 @@ k_posterior_fast_dc(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   constexpr int NSTA = 3, NSTB = 3;
   constexpr int GEN_THREADS = 256;
   constexpr int CW = 256, NSLOT = 2, KSH = 2;
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(CW >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(CW >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = prm.gp.d, np = prm.gp.n_pad;
   const int nkb = np / FK;
@@ -222,7 +222,7 @@ k_posterior_fast_dc(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       }
       const long long cg = tile * FM + row;
       if (cg < prm.m) {
-        double v = prm.gp.sigma_f2 - ss;
+        double v = prm.gp.sigma_f2 - ss * prm.gp.bscale[2];      // ss = s^2 ||L^-1 k*||^2
         prm.var_out[cg] = fmax(v, prm.gp.var_floor) + prm.gp.sigma_n2;
       }
     }
@@ -260,6 +260,29 @@ k_posterior_fast_dc(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     float mu_acc[4];
     // distance phase: r^2 = |a|^2 + |b|^2 + sum_j (-2 a_j) b_j on centred scaled inputs
     auto dist = [&](const float *xs, const float (&x)[R][DP], const float (&a2)[R], float2 (&r2)[R][4]) __attribute__((always_inline)) {
+      if (prm.gp.flags & OMBO_GP_DIRECT_DISTANCES) {
+        // direct differences: (b_j - a_j)^2 summed, no |a|^2 + |b|^2 - 2 a.b cancellation (ill-conditioned GPs)
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) r2[rr][e] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < DP; ++j) {
+          const float4 t0 = *(const float4 *)(xs + j * FK);
+          const float4 t1 = *(const float4 *)(xs + j * FK + 4);
+#pragma unroll
+          for (int rr = 0; rr < R; ++rr) {
+            const float2 xx = make_float2(x[rr][j], x[rr][j]), hh = make_float2(0.5f, 0.5f);   // x = -2 a_j
+            const float2 d0 = __ffma2_rn(xx, hh, make_float2(t0.x, t0.y)), d1 = __ffma2_rn(xx, hh, make_float2(t0.z, t0.w));
+            const float2 d2 = __ffma2_rn(xx, hh, make_float2(t1.x, t1.y)), d3 = __ffma2_rn(xx, hh, make_float2(t1.z, t1.w));
+            r2[rr][0] = __ffma2_rn(d0, d0, r2[rr][0]);
+            r2[rr][1] = __ffma2_rn(d1, d1, r2[rr][1]);
+            r2[rr][2] = __ffma2_rn(d2, d2, r2[rr][2]);
+            r2[rr][3] = __ffma2_rn(d3, d3, r2[rr][3]);
+          }
+        }
+        return;
+      }
       const float4 n0 = *(const float4 *)(xs + (DP + 1) * FK);
       const float4 n1 = *(const float4 *)(xs + (DP + 1) * FK + 4);
 #pragma unroll
@@ -326,10 +349,10 @@ k_posterior_fast_dc(const __grid_constant__ CUtensorMap map_hi, const __grid_con
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            __nv_bfloat162 h = __float22bfloat162_rn(kv[e]);
+            __half2 h = __float22half2_rn(kv[e]);
             const uint32_t hb = *reinterpret_cast<uint32_t *>(&h);
-            const float2 hf = make_float2(__uint_as_float(hb << 16), __uint_as_float(hb & 0xffff0000u));
-            __nv_bfloat162 l = __float22bfloat162_rn(__ffma2_rn(hf, make_float2(-1.0f, -1.0f), kv[e]));   // k' - hi, exact
+            const float2 hf = __half22float2(h);
+            __half2 l = __float22half2_rn(__ffma2_rn(hf, make_float2(-1.0f, -1.0f), kv[e]));   // k' - hi, exact
             hi[e] = hb;
             lo[e] = *reinterpret_cast<uint32_t *>(&l);
           }

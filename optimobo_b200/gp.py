@@ -97,8 +97,8 @@ class GPModel:
         return self
 
     # fast precision mode keeps sigma within 1e-3 sigma_f while `conditioning` stays below this (measured,
-    # scripts/cond_study.py: the error grows from 6e-5 sigma_f at 15 to 4e-3 at 8e3 and 4e-2 at 4e7)
-    FAST_MODE_CONDITIONING_LIMIT = 1.0e3
+    # scripts/cond_study.py: the error grows from 4e-5 sigma_f at 15 to 2.4e-4 at 4e2, 1e-3 at 4e3-8e3, 1.5e-2 at 4e7)
+    FAST_MODE_CONDITIONING_LIMIT = 2.0e3
 
     @property
     def conditioning(self):
@@ -133,7 +133,10 @@ class GPModel:
     def c_struct(self, var_floor=1e-15):
         if not self.refreshed:
             raise RuntimeError("GPModel.refresh() has not been run")
-        return _cabi.Gp(n=self.n, d=self.d, kernel=self.kernel, reserved=0, sigma_f2=self.variance,
+        # bit 0 (OMBO_GP_DIRECT_DISTANCES): the fast mode's FP32 |a|^2 + |b|^2 - 2 a.b distance form loses digits to
+        # cancellation, which an ill-conditioned factor amplifies; beyond kappa = 100 it uses direct differences
+        flags = 1 if self.conditioning > 100.0 else 0
+        return _cabi.Gp(n=self.n, d=self.d, kernel=self.kernel, reserved=flags, sigma_f2=self.variance,
                         sigma_n2=self.noise, var_floor=var_floor, state=self.state.data_ptr())
 
     # ---- the two model surfaces ------------------------------------------------------------

@@ -374,7 +374,7 @@ def test_errors_are_loud():
 
 
 # ------------------------------------------------------------------------------------------
-# fast mode: bf16x3 split on tcgen05 (rtol 1e-3, north_star; atol 1e-3 of the output scale
+# fast mode: fp16x3 split on tcgen05 (rtol 1e-3, north_star; atol 1e-3 of the output scale
 # because sigma -> 0 / mu -> 0 make a pure relative bound meaningless)
 # ------------------------------------------------------------------------------------------
 FAST_CASES = [(128, 10, 1000), (256, 10, 1 << 14), (512, 12, 1 << 13), (1024, 10, 1 << 13), (700, 7, 5001),
@@ -648,7 +648,7 @@ def test_conditioning_proxy_guards_the_fast_mode():
     for gp, X, ell in ((good, good_X, 0.7), (bad, bad_X, 0.3)):
         dg = np.diag(O.gp_fit_state(X, y, ell * np.ones(X.shape[1]), 1.5, form="direct")["L"])
         assert gp.conditioning == pytest.approx((dg.max() / dg.min()) ** 2, rel=1e-6)
-    assert good.conditioning < 1e3 < bad.conditioning
+    assert good.conditioning < ob.GPModel.FAST_MODE_CONDITIONING_LIMIT < bad.conditioning
     base = PoolOptimiserBase(Problem(n_var=10, n_obj=2, xl=np.zeros(10), xu=np.ones(10)), device=DEV)
     if _cabi.fast_path_available():
         assert base._precision_for([good]) == "fast" and base._precision_for([bad]) == "fp64"
