@@ -314,7 +314,7 @@ def main():
         pass
     if precision == "fast":
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step; fp16 and bf16 share the kind::f16 rate)"
+        peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                     if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)")
     else:
         # no FP64 peak in MEASURED_PEAKS.json: measure cuBLAS DGEMM here
@@ -346,14 +346,14 @@ def main():
                 "kernel_share_of_step": prof_ms / total_ms if total_ms else None,
                 "flops_per_candidate": fl_cand}
     if precision == "fast" and achieved:
-        # what the tensor cores actually execute: 3 fp16 products per split-precision MAC, and the 128-wide
+        # what the tensor cores actually execute: 3 16-bit products per split-precision MAC, and the 128-wide
         # diagonal blocks of the triangular factor are multiplied densely (68 of 64 ideal units at n = 1024)
         nch = N_TRAIN // 128
         units = sum(2 * c + 2 for c in range(nch)) - 0.5 * nch
         issued = 3 * units * (128 * 64) * 2              # FLOP per candidate per GP: units of 128 columns x 64 K
         issued_tflops = issued * cand_per_launch / (launch_ms / 1e3) / 1e12
         roofline["issued"] = {"tflops": issued_tflops, "frac": issued_tflops / peak,
-                              "note": "fp16x3 split: 3 tensor-core products per algorithmic MAC, "
+                              "note": "bf16x3 split (fp16x3 planes for ill-conditioned GPs): 3 tensor-core products per algorithmic MAC, "
                                       "diagonal blocks dense; this is the tensor-pipe work the kernel sustains"}
 
     cpu = None
@@ -367,7 +367,7 @@ def main():
         "metric": "candidates scored/sec (GP mean+std+EHVI)", "value": value, "unit": "candidates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "fp16x3" if precision == "fast" else "f64", "data": "synthetic",
+        "dtype": "bf16x3" if precision == "fast" else "f64", "data": "synthetic",
         "config": {"workload": f"C5: n_train={n} d={d} k=2, full posterior + EHVI-2D ({args.semantics} semantics) + arg-max",
                    "candidates_per_gpu_per_step": m_per_gpu, "precision": precision,
                    "l2": "256 MB flush between timed iterations",

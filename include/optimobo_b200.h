@@ -50,7 +50,7 @@ extern "C" {
 
 enum { OMBO_KERNEL_MATERN52 = 0, OMBO_KERNEL_RBF = 1 };
 enum { OMBO_PREC_FP64 = 0,   /* FP64 DMMA path, reference-tolerance mode (rtol 1e-6)    */
-       OMBO_PREC_FAST = 1 }; /* fp16x3 split on tcgen05 tensor cores (rtol 1e-3)        */
+       OMBO_PREC_FAST = 1 }; /* 16-bit x3 split on tcgen05 tensor cores (rtol 1e-3)     */
 enum { OMBO_SEM_REFERENCE = 0, /* reproduces the reference's formulas incl. quirks       */
        OMBO_SEM_EXACT = 1 };   /* each model's own sigma, n+1 EHVI stripes               */
 
@@ -93,8 +93,8 @@ enum { OMBO_FIELD_L = 0,      /* (n_pad, n_pad) f64 lower Cholesky factor       
        OMBO_FIELD_ALPHA = 2,  /* (n_pad,) f64                                             */
        OMBO_FIELD_XS = 3,     /* (d, n_pad) f64 length-scale-scaled training inputs       */
        OMBO_FIELD_STATUS = 4, /* (4,) i32: [0] = first non-PD pivot row + 1, 0 if PD       */
-       OMBO_FIELD_BHI = 5,    /* (n_pad, n_pad) fp16, hi plane of s * sigma_f2 * Linv      */
-       OMBO_FIELD_BLO = 6,    /* (n_pad, n_pad) fp16, lo plane (s: power-of-two scale)     */
+       OMBO_FIELD_BHI = 5,    /* (n_pad, n_pad) bf16 | fp16, hi plane of s*sigma_f2*Linv   */
+       OMBO_FIELD_BLO = 6,    /* (n_pad, n_pad) lo plane (format / scale chosen by K3)     */
        OMBO_FIELD_XS32 = 7,   /* (32, n_pad) f32 centred scaled training inputs (fast path) */
        OMBO_FIELD_ALPHA32 = 8 /* (n_pad,) f32 alpha * sigma_f2                              */
 };
@@ -123,9 +123,12 @@ int ombo_gp_refresh(ombo_ctx *ctx, const ombo_gp_spec *spec, void *state, void *
 int ombo_gp_nlml_grad(ombo_ctx *ctx, const ombo_gp_spec *spec, void *state, double *out_host, void *stream);
 
 /* ---- scoring --------------------------------------------------------------- */
-/* ombo_gp.reserved carries flags: bit 0 = fast mode computes the scaled distances by direct differences
- * (2 FMAs per dimension instead of 1, no cancellation: for ill-conditioned GPs) */
-#define OMBO_GP_DIRECT_DISTANCES 1
+/* ombo_gp.reserved carries the flags of the refreshed state.  ombo_gp_refresh chooses the format of the fast
+ * mode's operand planes on the device from the conditioning of the Cholesky factor -- bf16 (well conditioned) or
+ * scaled fp16 together with direct-difference distances (ill conditioned) -- and reports it in
+ * OMBO_FIELD_STATUS word 1 of the state blob (1 = fp16).  The caller copies it into bit 1 of `reserved`;
+ * the scoring entries launch the matching kernel instantiation. */
+#define OMBO_GP_FP16_PLANES 2
 typedef struct {
   int32_t n, d, kernel, reserved;
   double sigma_f2, sigma_n2;

@@ -115,7 +115,7 @@ class PoolOptimiserBase:
         d = models[0].d
         if not (_cabi.fast_path_available() and n > 256 and d <= 24):
             return "fp64"
-        # ... and large but ill-conditioned ones (many points per length-scale in few dimensions): the fp16x3
+        # ... and large but ill-conditioned ones (many points per length-scale in few dimensions): the 3-product
         # split then loses absolute accuracy on sigma (GPModel.conditioning, scripts/cond_study.py)
         from ..gp import GPModel
         return "fast" if max(m.conditioning for m in models) <= GPModel.FAST_MODE_CONDITIONING_LIMIT else "fp64"

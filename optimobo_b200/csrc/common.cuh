@@ -97,7 +97,7 @@ static inline GpLayout gp_layout(int n, int d) {
   L.off_alpha32 = take(np * 4);
   L.off_center = take((size_t)OMBO_MAX_DIM * 8);
   L.off_b2 = take(np * 4);
-  L.off_bscale = take(32);                // [0] max |sigma_f2 L^-1| (bits), [1] power-of-two scale s of the fp16 planes, [2] 1/s^2
+  L.off_bscale = take(32);                // after the refresh: [1] scale s of the 16-bit planes, [2] 1/s^2, [3] 1.0 = fp16 / 0.0 = bf16
   L.bytes = off;
   return L;
 }
@@ -111,8 +111,8 @@ struct GpDev {
   const double *ell;      // (d) length-scales
   const double *Linv;     // (n_pad, n_pad)
   const double *alpha;    // (n_pad)
-  const __half *bhi, *blo;               // fp16 hi / lo planes of s * sigma_f2 * L^-1
-  const double *bscale;                  // [1] = s, [2] = 1 / s^2 (power of two: exact)
+  const unsigned short *bhi, *blo;       // 16-bit hi / lo planes of s * sigma_f2 * L^-1 (bf16 or fp16, see bscale[3])
+  const double *bscale;                  // [1] = s, [2] = 1 / s^2 (power of two: exact), [3] = 1.0 fp16 / 0.0 bf16
   const float *xs32, *alpha32, *b2_32;   // fast path: centred scaled inputs, sigma_f2*alpha, |xs32_i|^2
   const double *center;                  // (d) per-dimension mean of the training inputs
 };
@@ -127,8 +127,8 @@ static inline GpDev gp_dev_view(const ombo_gp &g) {
   v.ell = (const double *)(b + L.off_inv_ell);
   v.Linv = (const double *)(b + L.off_Linv);
   v.alpha = (const double *)(b + L.off_alpha);
-  v.bhi = (const __half *)(b + L.off_bhi);
-  v.blo = (const __half *)(b + L.off_blo);
+  v.bhi = (const unsigned short *)(b + L.off_bhi);
+  v.blo = (const unsigned short *)(b + L.off_blo);
   v.bscale = (const double *)(b + L.off_bscale);
   v.xs32 = (const float *)(b + L.off_xs32);
   v.alpha32 = (const float *)(b + L.off_alpha32);

@@ -282,40 +282,69 @@ __global__ void k_trmv_lower_t(const double *__restrict__ M, int ld, int n_pad, 
   }
 }
 
-// max |L^-1| over the valid lower triangle (bit pattern of a non-negative double orders like the value)
-__global__ void k_absmax_lower(const double *__restrict__ Linv, int n, int n_pad, unsigned long long *__restrict__ out) {
+// max |L^-1| over the valid lower triangle and min / max of diag(L) (bit patterns of non-negative doubles order
+// like the values): out[0] = max |L^-1|, out[1] = max L_ii, out[2] = min L_ii (initialised to +inf bits by the host)
+__global__ void k_absmax_lower(const double *__restrict__ Linv, const double *__restrict__ L, int n, int n_pad,
+                               unsigned long long *__restrict__ out) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   double v = 0.0;
   if (e < (size_t)n_pad * n_pad) {
     const int j = (int)(e / n_pad), i = (int)(e % n_pad);
     if (j < n && i <= j) v = fabs(Linv[e]);
+    if (j < n && i == j) {
+      const unsigned long long dg = (unsigned long long)__double_as_longlong(fabs(L[e]));
+      atomicMax(out + 1, dg);
+      atomicMin(out + 2, dg);
+    }
   }
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(v));
 }
 
-// zero the padding of L^-1 and emit the fast-path operands:
-//   B = s * sigma_f2 * L^-1 split into fp16 hi + lo planes (s = the power of two that brings max |B| to
-//   [8192, 16384): fp16 has 11 significant bits against bf16's 8, so the 3-product split carries 22 bits,
-//   and the scale keeps ill-conditioned factors inside its range), alpha32 = sigma_f2 * alpha
+// zero the padding of L^-1 and emit the fast-path operands B = s * sigma_f2 * L^-1 as 16-bit hi + lo planes.
+// The format is chosen here, on the device, from the conditioning proxy kappa = (max L_ii / min L_ii)^2:
+//   kappa <= 100: bf16 planes, s = 1 (8 significant bits each, 16 in the 3-product split: sigma good to 1e-4 sigma_f
+//                 at that conditioning, and the tensor core runs bf16 ~3.5 % faster than fp16 at the power cap);
+//   kappa  > 100: fp16 planes (11 + 11 bits), s = the power of two that brings max |B| into [8192, 16384) so that
+//                 ill-conditioned factors stay inside fp16's range; the generators then also use direct-difference
+//                 distances.  bscale[1] = s, [2] = 1 / s^2, [3] = 1.0 for fp16 / 0.0 for bf16.
 __global__ void k_finalize(double *__restrict__ Linv, int n, int n_pad, double sf2,
-                           __half *__restrict__ bhi, __half *__restrict__ blo, double *__restrict__ bscale,
+                           unsigned short *__restrict__ bhi, unsigned short *__restrict__ blo, double *__restrict__ bscale,
                            const double *__restrict__ alpha, float *__restrict__ alpha32) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)n_pad * n_pad;
   if (e >= total) return;
-  const double mx = bscale[0] * sf2;                       // bscale[0] holds the double written by k_absmax_lower
-  const double sc = mx > 0.0 ? exp2(floor(log2(16384.0 / mx))) : 1.0;
-  if (e == 0) { bscale[1] = sc; bscale[2] = 1.0 / (sc * sc); }
+  const double ratio = bscale[2] > 0.0 ? bscale[1] / bscale[2] : 1.0;       // max L_ii / min L_ii
+  const bool f16 = ratio * ratio > 100.0;
+  const double mx = bscale[0] * sf2;
+  const double sc = (f16 && mx > 0.0) ? exp2(floor(log2(16384.0 / mx))) : 1.0;
   int j = (int)(e / n_pad), i = (int)(e % n_pad);
   double v = Linv[e];
   if (j >= n || i >= n || i > j) { v = 0.0; Linv[e] = 0.0; }
   const double t = v * sf2 * sc;
-  const __half h = __float2half_rn((float)t);
-  const float rem = (float)(t - (double)__half2float(h));
-  bhi[e] = h;
-  blo[e] = __float2half_rn(rem);
+  if (f16) {
+    const __half h = __float2half_rn((float)t);
+    const __half l = __float2half_rn((float)(t - (double)__half2float(h)));
+    bhi[e] = __half_as_ushort(h);
+    blo[e] = __half_as_ushort(l);
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn((float)t);
+    const __nv_bfloat16 l = __float2bfloat16_rn((float)(t - (double)__bfloat162float(h)));
+    bhi[e] = __bfloat16_as_ushort(h);
+    blo[e] = __bfloat16_as_ushort(l);
+  }
   if (e < (size_t)n_pad) alpha32[e] = (float)(alpha[e] * sf2);
+}
+
+// the per-GP constants the fast kernels read: [1] = s, [2] = 1 / s^2, [3] = format flag (after every thread of
+// k_finalize has read the raw extrema: a separate launch)
+__global__ void k_publish_scale(double *__restrict__ bscale, double sf2, int *__restrict__ status) {
+  const double ratio = bscale[2] > 0.0 ? bscale[1] / bscale[2] : 1.0;
+  const bool f16 = ratio * ratio > 100.0;
+  const double mx = bscale[0] * sf2;
+  const double sc = (f16 && mx > 0.0) ? exp2(floor(log2(16384.0 / mx))) : 1.0;
+  bscale[1] = sc; bscale[2] = 1.0 / (sc * sc); bscale[3] = f16 ? 1.0 : 0.0;
+  status[1] = f16 ? 1 : 0;            // read back by the host with the PD flag: OMBO_GP_FP16_PLANES for ombo_gp.reserved
 }
 
 // ------------------------------------------------------------------------------------------
@@ -354,7 +383,7 @@ int ombo_refresh_impl(ombo_ctx *ctx, const ombo_gp_spec *sp, void *state, cudaSt
   int *status = (int *)(b + lay.off_status);
   double *dinv = (double *)(b + lay.off_dinv), *tmp = (double *)(b + lay.off_tmp);
   double *ell_dev = (double *)(b + lay.off_inv_ell);
-  __half *bhi = (__half *)(b + lay.off_bhi), *blo = (__half *)(b + lay.off_blo);
+  unsigned short *bhi = (unsigned short *)(b + lay.off_bhi), *blo = (unsigned short *)(b + lay.off_blo);
   double *bscale = (double *)(b + lay.off_bscale);
   float *xs32 = (float *)(b + lay.off_xs32), *alpha32 = (float *)(b + lay.off_alpha32);
   float *b2 = (float *)(b + lay.off_b2);
@@ -376,10 +405,14 @@ int ombo_refresh_impl(ombo_ctx *ctx, const ombo_gp_spec *sp, void *state, cudaSt
   k_trmv_lower<<<(np + 7) / 8, 256, 0, s>>>(Linv, np, np, alpha, tmp);
   k_trmv_lower_t<<<(np + 31) / 32, dim3(32, 8), 0, s>>>(Linv, np, np, tmp, alpha);
   size_t total = (size_t)np * np;
-  OMBO_CUDA(cudaMemsetAsync(bscale, 0, 32, s));
-  k_absmax_lower<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Linv, n, np, (unsigned long long *)bscale);
+  {
+    static const unsigned long long init[4] = {0ull, 0ull, 0x7ff0000000000000ull, 0ull};      // max, max, min (+inf), -
+    OMBO_CUDA(cudaMemcpyAsync(bscale, init, 32, cudaMemcpyHostToDevice, s));
+  }
+  k_absmax_lower<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Linv, L, n, np, (unsigned long long *)bscale);
   k_finalize<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Linv, n, np, sp->sigma_f2, bhi, blo, bscale, alpha, alpha32);
-  ctx->launches += 5;
+  k_publish_scale<<<1, 1, 0, s>>>(bscale, sp->sigma_f2, status);
+  ctx->launches += 6;
   OMBO_CUDA(cudaGetLastError());
   int hstatus[4] = {0, 0, 0, 0};
   OMBO_CUDA(cudaMemcpyAsync(hstatus, status, 16, cudaMemcpyDeviceToHost, s));

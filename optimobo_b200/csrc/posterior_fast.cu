@@ -2,7 +2,8 @@
 // Same contract as posterior_fp64.cu (mu, var per candidate for one GP), tolerance rtol 1e-3.
 //
 //   V = K* . (sigma_f2 L^-1)^T     K* = k'(r) in (0,1] generated ON CHIP, never touching HBM
-//   A = K*  = A_hi + A_lo (bf16),  B = sigma_f2 L^-1 = B_hi + B_lo (bf16 planes from K3)
+//   A = K*  = A_hi + A_lo,  B = s sigma_f2 L^-1 = B_hi + B_lo (16-bit planes from K3: bf16, or scaled fp16 for
+//   ill-conditioned GPs -- template parameter F16, selected from ombo_gp.reserved)
 //   V ~= A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T      (three kind::f16 MMAs, FP32 accumulate in TMEM)
 //   var = sigma_f2 - sum_j V_j^2 (V = L^-1 k*),  mu = sum_i k'_i (sigma_f2 alpha_i) on the CUDA cores.
 //
@@ -39,7 +40,7 @@
 //        2: single CTA, 256-column chunks (half the A re-reads per MAC; the diagonal K-blocks shrink N to
 //           192 / 128 / 64), B ring entries are single planes so the lo plane of a unit can still be in
 //           flight while its hi plane is being multiplied -- the default
-template <int DP, int R, int MODE, int GW>
+template <int DP, int R, int MODE, int GW, bool F16>
 __global__ void __launch_bounds__((8 + GW) * 32, 1)
 k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                  const __grid_constant__ CUtensorMap map_kc, const FastParams prm) {
@@ -175,6 +176,8 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     // =============================== MMA issuer (leader CTA only in PAIR mode) ============
     if (!mo && leader && elect_one()) {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, tph = 0;   // tph: per-slot phase bits of t_empty
+      // operand format chosen by K3 on the device (bscale[3]): bf16 planes for well-conditioned GPs, fp16 otherwise
+      constexpr uint32_t IDESC_RT = IDESC | (F16 ? 0u : ((1u << 7) | (1u << 10)));
       long long w_afull = 0, w_bfull = 0, w_tempty = 0; const bool pon = prm.prof != nullptr;
       for (long long it = 0; it < n_iter; ++it) {
         for (int p = 0; p < n_pass; ++p) {
@@ -195,7 +198,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                 // rows of the chunk above the diagonal band are zero: skip them (N = 256, 192, 128 or 64)
                 const int r0 = max(0, kb - 4 * c) * 64;
                 const uint32_t dcolw = tmem_base + (uint32_t)(slot * CW + r0);
-                const uint32_t idw = (IDESC & ~(0x3Fu << 17)) | ((uint32_t)((CW - r0) >> 3) << 17);
+                const uint32_t idw = (IDESC_RT & ~(0x3Fu << 17)) | ((uint32_t)((CW - r0) >> 3) << 17);
                 // hi plane: A_hi.B_hi and A_lo.B_hi
                 mbar_wait_prof(smem_u32(&b_full[sb]), pb, MMA_SLEEP_NS, w_bfull, pon);
                 tc_fence_after();
@@ -228,12 +231,12 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
               tc_fence_after();
               uint32_t b_hi = smem_u32(sB + sb * STAGE_BYTES), b_lo = b_hi + PLANE_BYTES;
               uint32_t dcol = tmem_base + (uint32_t)(slot * CW);
-              uint32_t idesc = IDESC;
+              uint32_t idesc = IDESC_RT;
               if (!PAIR && kb == 2 * c + 1) {
                 // second K-block of the diagonal 128x128 block: rows 0..63 of the chunk lie above the
                 // diagonal (zero), so only the lower 64 accumulator columns are touched: N = 64 UMMA
                 b_hi += 64 * 128; b_lo += 64 * 128; dcol += 64;
-                idesc = (IDESC & ~(0x3Fu << 17)) | ((uint32_t)(64 >> 3) << 17);
+                idesc = (IDESC_RT & ~(0x3Fu << 17)) | ((uint32_t)(64 >> 3) << 17);
               }
               if (!(prm.dbg & 1)) {
 #pragma unroll
@@ -317,6 +320,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     const int q = (gt >> 5) & 7;                 // operand chunk 0..7 of this warp
     const int rh = gt >> 8;                      // row half (GW = 16 only)
     const bool matern = (prm.gp.kernel == OMBO_KERNEL_MATERN52);
+    constexpr bool f16 = F16, direct = F16;         // fp16 planes (ill-conditioned GP): fp16 split + direct distances
     constexpr int RB = 128 / (32 * R * (GW / 8));   // row batches per K-block
     constexpr int ROW0 = R * RB;                  // rows (in units of 32) owned by one row half
     constexpr int XT_STRIDE = (DP + 2) * FK;
@@ -425,7 +429,7 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
               }
             }
             float2 r2[R][4];
-            if (prm.gp.flags & OMBO_GP_DIRECT_DISTANCES) {
+            if (direct) {
               // direct differences: (b_j - a_j)^2 summed, no |a|^2 + |b|^2 - 2 a.b cancellation (ill-conditioned GPs)
 #pragma unroll
               for (int rr = 0; rr < R; ++rr)
@@ -511,14 +515,24 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
               }
               if (!mo) {
               uint32_t hi[4], lo[4];
+              if (f16) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                __half2 h = __float22half2_rn(kv[e]);
-                const uint32_t hb = *reinterpret_cast<uint32_t *>(&h);
-                const float2 hf = __half22float2(h);
-                __half2 l = __float22half2_rn(__ffma2_rn(hf, make_float2(-1.0f, -1.0f), kv[e]));   // k' - hi, exact
-                hi[e] = hb;
-                lo[e] = *reinterpret_cast<uint32_t *>(&l);
+                for (int e = 0; e < 4; ++e) {
+                  __half2 h = __float22half2_rn(kv[e]);
+                  __half2 l = __float22half2_rn(__ffma2_rn(__half22float2(h), make_float2(-1.0f, -1.0f), kv[e]));   // k' - hi, exact
+                  hi[e] = *reinterpret_cast<uint32_t *>(&h);
+                  lo[e] = *reinterpret_cast<uint32_t *>(&l);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  __nv_bfloat162 h = __float22bfloat162_rn(kv[e]);
+                  const uint32_t hb = *reinterpret_cast<uint32_t *>(&h);
+                  const float2 hf = make_float2(__uint_as_float(hb << 16), __uint_as_float(hb & 0xffff0000u));
+                  __nv_bfloat162 l = __float22bfloat162_rn(__ffma2_rn(hf, make_float2(-1.0f, -1.0f), kv[e]));
+                  hi[e] = hb;
+                  lo[e] = *reinterpret_cast<uint32_t *>(&l);
+                }
               }
               const int row = lane + 32 * (ROW0 * rh + R * rb + rr);
               const uint32_t off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((q ^ (row & 7)) & 7) << 4));
@@ -622,14 +636,14 @@ static int make_linear_map(CUtensorMap *map, const void *base, size_t rows) {
 
 int ombo_fast_path_built() { return 1; }
 
-template <int DP, int R, int MODE, int GW>
+template <int DP, int R, int MODE, int GW, bool F16>
 static int launch_fast(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensorMap &map_lo, const CUtensorMap &map_kc, const FastParams &prm,
                        int grid, int cs, cudaStream_t s) {
   const size_t smem = (size_t)6 * STAGE_BYTES + (size_t)DP * FM * 4 + 2 * (size_t)(DP + 2) * FK * 4 +
                       8 * FM * 4 + 16 + 24 * 8 + 24 * 8 + 1024;   // barriers + TMEM slot, 1/lengthscale, alignment slack
   static bool attr = false;
   if (!attr) {
-    OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast<DP, R, MODE, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast<DP, R, MODE, GW, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   ProfScope prof(ctx, s);
@@ -643,7 +657,7 @@ static int launch_fast(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensorM
   at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  OMBO_CUDA(cudaLaunchKernelEx(&cfg, k_posterior_fast<DP, R, MODE, GW>, map_hi, map_lo, map_kc, prm));
+  OMBO_CUDA(cudaLaunchKernelEx(&cfg, k_posterior_fast<DP, R, MODE, GW, F16>, map_hi, map_lo, map_kc, prm));
   return OMBO_OK;
 }
 
@@ -709,11 +723,13 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
   const int d = gp.d;
   // (16 generator warps with 2 rows per lane were measured too: the same number of independent chains per
   // scheduler, no gain -- the instantiations were dropped to keep the build short)
-#define FAST_DISPATCH(DPV, RV)                                                                  \
-  rc = dc ? ombo_launch_fast_dc(ctx, map_hi, map_lo, map_kc, prm, grid, s)                        \
-     : pair ? launch_fast<DPV, RV, 1, 8>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)           \
-     : wide ? launch_fast<DPV, RV, 2, 8>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)           \
-            : launch_fast<DPV, RV, 0, 8>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)
+  const bool f16 = (gp.flags & OMBO_GP_FP16_PLANES) != 0;     // format of the planes, as reported by the refresh
+#define FAST_DISPATCH_F(DPV, RV, FV)                                                                  \
+  rc = dc ? ombo_launch_fast_dc(ctx, map_hi, map_lo, map_kc, prm, grid, s)                              \
+     : pair ? launch_fast<DPV, RV, 1, 8, FV>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)             \
+     : wide ? launch_fast<DPV, RV, 2, 8, FV>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)             \
+            : launch_fast<DPV, RV, 0, 8, FV>(ctx, map_hi, map_lo, map_kc, prm, grid, cs, s)
+#define FAST_DISPATCH(DPV, RV) do { if (f16) { FAST_DISPATCH_F(DPV, RV, true); } else { FAST_DISPATCH_F(DPV, RV, false); } } while (0)
   if (d <= 2) { FAST_DISPATCH(2, 4); }
   else if (d <= 4) { FAST_DISPATCH(4, 4); }
   else if (d <= 6) { FAST_DISPATCH(6, 4); }
@@ -723,6 +739,7 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
   else if (d <= 16) { FAST_DISPATCH(16, 2); }
   else { FAST_DISPATCH(24, 2); }
 #undef FAST_DISPATCH
+#undef FAST_DISPATCH_F
   if (rc) return rc;
   ctx->launches += 1;
   OMBO_CUDA(cudaGetLastError());

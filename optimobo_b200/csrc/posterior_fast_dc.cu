@@ -39,7 +39,7 @@ __device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.relaxed.cluster.shared::cluster.u32 [%0], %1;\n" ::"r"(addr), "r"(v) : "memory");
 }
 
-template <int DP, int R>
+template <int DP, int R, bool F16>
 __global__ void __launch_bounds__(16 * 32, 1)
 k_posterior_fast_dc(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                     const __grid_constant__ CUtensorMap map_kc, const FastParams prm) {
@@ -149,6 +149,7 @@ k_posterior_fast_dc(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     // =============================== MMA issuer (leader) ==================================
     if (!mo && leader && elect_one()) {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, tph = 0, fills = 0;
+      constexpr uint32_t IDESC_RT = IDESC | (F16 ? 0u : ((1u << 7) | (1u << 10)));   // bf16 / fp16 planes
       const uint32_t landed_peer = mapa_rank(smem_u32(landed), 1);
       long long w_afull = 0, w_bfull = 0, w_tempty = 0;
       for (long long it = 0; it < n_iter; ++it)
@@ -178,9 +179,9 @@ k_posterior_fast_dc(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                 for (int ks = 0; ks < FK / 16; ++ks) {
                   const uint64_t dah = make_sdesc(a_hi + ks * 32), dal = make_sdesc(a_lo + ks * 32);
                   const uint64_t dbh = make_sdesc(b_hi + ks * 32), dbl = make_sdesc(b_lo + ks * 32);
-                  umma_bf16_2sm(dcol, dah, dbh, IDESC, (kb > 0 || ks > 0) ? 1u : 0u);
-                  umma_bf16_2sm(dcol, dal, dbh, IDESC, 1u);
-                  umma_bf16_2sm(dcol, dah, dbl, IDESC, 1u);
+                  umma_bf16_2sm(dcol, dah, dbh, IDESC_RT, (kb > 0 || ks > 0) ? 1u : 0u);
+                  umma_bf16_2sm(dcol, dal, dbh, IDESC_RT, 1u);
+                  umma_bf16_2sm(dcol, dah, dbl, IDESC_RT, 1u);
                 }
               }
               umma_commit_2sm(smem_u32(&b_empty[sb]));
@@ -238,6 +239,7 @@ k_posterior_fast_dc(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     const int q = lane & 7;
     const int row0 = 16 * (gt >> 5) + (lane >> 3);       // this thread's rows: row0 + 4 i, i = 0..3
     const bool matern = (prm.gp.kernel == OMBO_KERNEL_MATERN52);
+    constexpr bool f16 = F16, direct = F16;         // fp16 planes (ill-conditioned GP): fp16 split + direct distances
     constexpr int RB = 128 / (32 * R);
     const bool ahead = (RB == 1) && ((gt >> 5) < 4);
     constexpr int XT_STRIDE = (DP + 2) * FK;
@@ -260,7 +262,7 @@ k_posterior_fast_dc(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     float mu_acc[4];
     // distance phase: r^2 = |a|^2 + |b|^2 + sum_j (-2 a_j) b_j on centred scaled inputs
     auto dist = [&](const float *xs, const float (&x)[R][DP], const float (&a2)[R], float2 (&r2)[R][4]) __attribute__((always_inline)) {
-      if (prm.gp.flags & OMBO_GP_DIRECT_DISTANCES) {
+      if (direct) {
         // direct differences: (b_j - a_j)^2 summed, no |a|^2 + |b|^2 - 2 a.b cancellation (ill-conditioned GPs)
 #pragma unroll
         for (int rr = 0; rr < R; ++rr)
@@ -347,14 +349,24 @@ k_posterior_fast_dc(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         }
         if (!mo) {
           uint32_t hi[4], lo[4];
+          if (f16) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __half2 h = __float22half2_rn(kv[e]);
-            const uint32_t hb = *reinterpret_cast<uint32_t *>(&h);
-            const float2 hf = __half22float2(h);
-            __half2 l = __float22half2_rn(__ffma2_rn(hf, make_float2(-1.0f, -1.0f), kv[e]));   // k' - hi, exact
-            hi[e] = hb;
-            lo[e] = *reinterpret_cast<uint32_t *>(&l);
+            for (int e = 0; e < 4; ++e) {
+              __half2 h = __float22half2_rn(kv[e]);
+              __half2 l = __float22half2_rn(__ffma2_rn(__half22float2(h), make_float2(-1.0f, -1.0f), kv[e]));   // k' - hi, exact
+              hi[e] = *reinterpret_cast<uint32_t *>(&h);
+              lo[e] = *reinterpret_cast<uint32_t *>(&l);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 h = __float22bfloat162_rn(kv[e]);
+              const uint32_t hb = *reinterpret_cast<uint32_t *>(&h);
+              const float2 hf = make_float2(__uint_as_float(hb << 16), __uint_as_float(hb & 0xffff0000u));
+              __nv_bfloat162 l = __float22bfloat162_rn(__ffma2_rn(hf, make_float2(-1.0f, -1.0f), kv[e]));
+              hi[e] = hb;
+              lo[e] = *reinterpret_cast<uint32_t *>(&l);
+            }
           }
           const int row = row0 + 4 * (R * rb + rr);
           const uint32_t off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((q ^ (row & 7)) & 7) << 4));
@@ -460,14 +472,14 @@ k_posterior_fast_dc(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u));
 }
 
-template <int DP, int R>
+template <int DP, int R, bool F16>
 static int launch_fast_dc(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensorMap &map_lo, const CUtensorMap &map_kc,
                           const FastParams &prm, int grid, cudaStream_t s) {
   const size_t smem = (size_t)6 * STAGE_BYTES + (size_t)DP * FM * 4 + 3 * (size_t)(DP + 2) * FK * 4 +
                       16 + 24 * 8 + 24 * 8 + 1024;     // barriers + counters, 1/lengthscale, alignment slack
   static bool attr = false;
   if (!attr) {
-    OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast_dc<DP, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast_dc<DP, R, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   ProfScope prof(ctx, s);
@@ -481,7 +493,7 @@ static int launch_fast_dc(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtens
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  OMBO_CUDA(cudaLaunchKernelEx(&cfg, k_posterior_fast_dc<DP, R>, map_hi, map_lo, map_kc, prm));
+  OMBO_CUDA(cudaLaunchKernelEx(&cfg, k_posterior_fast_dc<DP, R, F16>, map_hi, map_lo, map_kc, prm));
   return OMBO_OK;
 }
 
@@ -489,12 +501,12 @@ int ombo_launch_fast_dc(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensor
                         const FastParams &prm, int grid, cudaStream_t s) {
   // 4 candidate rows x d coordinates live in registers: d <= 12 (larger d runs the single-CTA kernel)
   const int d = prm.gp.d;
-  if (d <= 2) return launch_fast_dc<2, 4>(ctx, map_hi, map_lo, map_kc, prm, grid, s);
-  if (d <= 4) return launch_fast_dc<4, 4>(ctx, map_hi, map_lo, map_kc, prm, grid, s);
-  if (d <= 6) return launch_fast_dc<6, 4>(ctx, map_hi, map_lo, map_kc, prm, grid, s);
-  if (d <= 8) return launch_fast_dc<8, 4>(ctx, map_hi, map_lo, map_kc, prm, grid, s);
-  if (d <= 10) return launch_fast_dc<10, 4>(ctx, map_hi, map_lo, map_kc, prm, grid, s);
-  if (d <= 12) return launch_fast_dc<12, 4>(ctx, map_hi, map_lo, map_kc, prm, grid, s);
+  const bool f16 = (prm.gp.flags & OMBO_GP_FP16_PLANES) != 0;
+#define DC_CASE(DPV)                                                                                     \
+  if (d <= DPV) return f16 ? launch_fast_dc<DPV, 4, true>(ctx, map_hi, map_lo, map_kc, prm, grid, s)      \
+                           : launch_fast_dc<DPV, 4, false>(ctx, map_hi, map_lo, map_kc, prm, grid, s)
+  DC_CASE(2); DC_CASE(4); DC_CASE(6); DC_CASE(8); DC_CASE(10); DC_CASE(12);
+#undef DC_CASE
   ombo_set_error("internal: decoupled fast kernel is instantiated for d <= 12 only");
   return OMBO_ERR_UNSUPPORTED;
 }

@@ -94,6 +94,9 @@ class GPModel:
         self.effective_jitter = jitter
         self.refreshed = True
         self._conditioning = None
+        # word 1 of the status field: the refresh stored fp16 (1) or bf16 (0) operand planes for the fast mode
+        st = self._field(_cabi.FIELD_STATUS, torch.int32, (4,)).cpu()
+        self._flags = 2 if int(st[1]) else 0          # OMBO_GP_FP16_PLANES
         return self
 
     # fast precision mode keeps sigma within 1e-3 sigma_f while `conditioning` stays below this (measured,
@@ -133,10 +136,8 @@ class GPModel:
     def c_struct(self, var_floor=1e-15):
         if not self.refreshed:
             raise RuntimeError("GPModel.refresh() has not been run")
-        # bit 0 (OMBO_GP_DIRECT_DISTANCES): the fast mode's FP32 |a|^2 + |b|^2 - 2 a.b distance form loses digits to
-        # cancellation, which an ill-conditioned factor amplifies; beyond kappa = 100 it uses direct differences
-        flags = 1 if self.conditioning > 100.0 else 0
-        return _cabi.Gp(n=self.n, d=self.d, kernel=self.kernel, reserved=flags, sigma_f2=self.variance,
+        # reserved = flags of the refreshed state (format of the fast mode's operand planes)
+        return _cabi.Gp(n=self.n, d=self.d, kernel=self.kernel, reserved=self._flags, sigma_f2=self.variance,
                         sigma_n2=self.noise, var_floor=var_floor, state=self.state.data_ptr())
 
     # ---- the two model surfaces ------------------------------------------------------------

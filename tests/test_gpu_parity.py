@@ -374,7 +374,7 @@ def test_errors_are_loud():
 
 
 # ------------------------------------------------------------------------------------------
-# fast mode: fp16x3 split on tcgen05 (rtol 1e-3, north_star; atol 1e-3 of the output scale
+# fast mode: 16-bit x3 split on tcgen05 (bf16 planes, fp16 for ill-conditioned GPs) (rtol 1e-3, north_star; atol 1e-3 of the output scale
 # because sigma -> 0 / mu -> 0 make a pure relative bound meaningless)
 # ------------------------------------------------------------------------------------------
 FAST_CASES = [(128, 10, 1000), (256, 10, 1 << 14), (512, 12, 1 << 13), (1024, 10, 1 << 13), (700, 7, 5001),
