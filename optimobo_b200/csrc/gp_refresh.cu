@@ -81,60 +81,9 @@ __global__ void k_build_K(const double *__restrict__ xs, int n, int d, int n_pad
   K[(size_t)i * n_pad + j] = v;
 }
 
-// ------------------------------------------------------------------------------------------
-// diagonal block: Cholesky of a 64x64 block + inverse of its triangular factor, 64 threads.
-// Thread t keeps ROW t of the block in registers (fully unrolled, compile-time register indices); per
-// elimination step only the current column travels through shared memory (two barriers of two warps),
-// so the 64 dependent steps cost ~100 cycles each instead of three 256-thread barriers + smem sweeps.
-__global__ void __launch_bounds__(64) k_potrf_diag(double *__restrict__ A, int ld, int kb, int n,
-                                                   double *__restrict__ dinv, int *__restrict__ status) {
-  __shared__ double Ls[NB][NB + 1];
-  __shared__ double col[NB];
-  __shared__ double pivot;
-  const int t = threadIdx.x;
-  double *blk = A + ((size_t)kb * NB) * ld + (size_t)kb * NB;
-  double a[NB];
-#pragma unroll
-  for (int k = 0; k < NB; ++k) a[k] = blk[(size_t)t * ld + k];
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    if (t == j) {
-      double p = a[j];
-      if (!(p > 0.0)) { atomicCAS(status, 0, kb * NB + j + 1); p = 1.0; }
-      pivot = sqrt(p);
-    }
-    __syncthreads();
-    const double piv = pivot;
-    if (t == j) a[j] = piv;
-    if (t > j) a[j] = a[j] / piv;
-    col[t] = a[j];                 // column j of L (entries t < j are never read)
-    __syncthreads();
-    if (t > j) {
-#pragma unroll
-      for (int k = j + 1; k < NB; ++k)
-        if (k <= t) a[k] -= a[j] * col[k];
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < NB; ++k) {
-    const double v = (k <= t) ? a[k] : 0.0;
-    Ls[t][k] = v;
-    blk[(size_t)t * ld + k] = v;
-  }
-  __syncthreads();
-  // inverse: thread t owns COLUMN t of X = L^-1 in registers; L is read from smem by broadcast
-  double x[NB];
-#pragma unroll
-  for (int i = 0; i < NB; ++i) {
-    double sacc = (i == t) ? 1.0 : 0.0;
-#pragma unroll
-    for (int k = 0; k < i; ++k)
-      if (k >= t) sacc -= Ls[i][k] * x[k];
-    x[i] = (i >= t) ? sacc / Ls[i][i] : 0.0;
-  }
-#pragma unroll
-  for (int i = 0; i < NB; ++i) dinv[(size_t)kb * NB * NB + (size_t)i * NB + t] = x[i];
-}
+// k_potrf_diag (Cholesky + inverse of one 64x64 diagonal block) lives in gp_potrf_diag.cu: its fully unrolled
+// 64-step register kernels take the NVVM optimiser five minutes at -O3 -- kept apart so that edits here build fast
+void ombo_launch_potrf_diag(double *A, int ld, int kb, int n, double *dinv, int *status, cudaStream_t s);
 
 // C(64x64) (+)= sign * As(64x64) * Bs(64x64)^T with both operands k-contiguous in smem
 __device__ __forceinline__ void gemm64_abt(double (*As)[LDS], double (*Bs)[LDS], double acc[4][4],
@@ -361,7 +310,7 @@ int ombo_potrf_lower_impl(ombo_ctx *ctx, double *L, int np, int n, double *dinv,
     attr_set = true;
   }
   for (int kb = 0; kb < nb; ++kb) {
-    k_potrf_diag<<<1, 64, 0, s>>>(L, np, kb, n, dinv, status);
+    ombo_launch_potrf_diag(L, np, kb, n, dinv, status, s);
     ctx->launches += 1;
     int rem = nb - kb - 1;
     if (rem > 0) {
