@@ -127,7 +127,9 @@ int ombo_gp_nlml_grad(ombo_ctx *ctx, const ombo_gp_spec *spec, void *state, doub
  * mode's operand planes on the device from the conditioning of the Cholesky factor -- bf16 (well conditioned) or
  * scaled fp16 together with direct-difference distances (ill conditioned) -- and reports it in
  * OMBO_FIELD_STATUS word 1 of the state blob (1 = fp16).  The caller copies it into bit 1 of `reserved`;
- * the scoring entries launch the matching kernel instantiation. */
+ * the scoring entries launch the matching kernel instantiation.  fp16 planes are only produced when the refresh
+ * was asked for them (ombo_gp_spec.reserved bit 1 set): a caller that leaves both `reserved` fields 0 always
+ * gets, and scores with, bf16 planes. */
 #define OMBO_GP_FP16_PLANES 2
 typedef struct {
   int32_t n, d, kernel, reserved;

@@ -257,14 +257,14 @@ __global__ void k_absmax_lower(const double *__restrict__ Linv, const double *__
 //   kappa  > 100: fp16 planes (11 + 11 bits), s = the power of two that brings max |B| into [8192, 16384) so that
 //                 ill-conditioned factors stay inside fp16's range; the generators then also use direct-difference
 //                 distances.  bscale[1] = s, [2] = 1 / s^2, [3] = 1.0 for fp16 / 0.0 for bf16.
-__global__ void k_finalize(double *__restrict__ Linv, int n, int n_pad, double sf2,
+__global__ void k_finalize(double *__restrict__ Linv, int n, int n_pad, double sf2, int allow_f16,
                            unsigned short *__restrict__ bhi, unsigned short *__restrict__ blo, double *__restrict__ bscale,
                            const double *__restrict__ alpha, float *__restrict__ alpha32) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)n_pad * n_pad;
   if (e >= total) return;
   const double ratio = bscale[2] > 0.0 ? bscale[1] / bscale[2] : 1.0;       // max L_ii / min L_ii
-  const bool f16 = ratio * ratio > 100.0;
+  const bool f16 = allow_f16 && ratio * ratio > 100.0;
   const double mx = bscale[0] * sf2;
   const double sc = (f16 && mx > 0.0) ? exp2(floor(log2(16384.0 / mx))) : 1.0;
   int j = (int)(e / n_pad), i = (int)(e % n_pad);
@@ -287,9 +287,9 @@ __global__ void k_finalize(double *__restrict__ Linv, int n, int n_pad, double s
 
 // the per-GP constants the fast kernels read: [1] = s, [2] = 1 / s^2, [3] = format flag (after every thread of
 // k_finalize has read the raw extrema: a separate launch)
-__global__ void k_publish_scale(double *__restrict__ bscale, double sf2, int *__restrict__ status) {
+__global__ void k_publish_scale(double *__restrict__ bscale, double sf2, int allow_f16, int *__restrict__ status) {
   const double ratio = bscale[2] > 0.0 ? bscale[1] / bscale[2] : 1.0;
-  const bool f16 = ratio * ratio > 100.0;
+  const bool f16 = allow_f16 && ratio * ratio > 100.0;
   const double mx = bscale[0] * sf2;
   const double sc = (f16 && mx > 0.0) ? exp2(floor(log2(16384.0 / mx))) : 1.0;
   bscale[1] = sc; bscale[2] = 1.0 / (sc * sc); bscale[3] = f16 ? 1.0 : 0.0;
@@ -358,9 +358,11 @@ int ombo_refresh_impl(ombo_ctx *ctx, const ombo_gp_spec *sp, void *state, cudaSt
     static const unsigned long long init[4] = {0ull, 0ull, 0x7ff0000000000000ull, 0ull};      // max, max, min (+inf), -
     OMBO_CUDA(cudaMemcpyAsync(bscale, init, 32, cudaMemcpyHostToDevice, s));
   }
+  // fp16 planes only for callers that announce (spec->reserved bit 1) that they will pass the reported format on
+  const int allow_f16 = (sp->reserved & OMBO_GP_FP16_PLANES) ? 1 : 0;
   k_absmax_lower<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Linv, L, n, np, (unsigned long long *)bscale);
-  k_finalize<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Linv, n, np, sp->sigma_f2, bhi, blo, bscale, alpha, alpha32);
-  k_publish_scale<<<1, 1, 0, s>>>(bscale, sp->sigma_f2, status);
+  k_finalize<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Linv, n, np, sp->sigma_f2, allow_f16, bhi, blo, bscale, alpha, alpha32);
+  k_publish_scale<<<1, 1, 0, s>>>(bscale, sp->sigma_f2, allow_f16, status);
   ctx->launches += 6;
   OMBO_CUDA(cudaGetLastError());
   int hstatus[4] = {0, 0, 0, 0};

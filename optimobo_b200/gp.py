@@ -79,7 +79,7 @@ class GPModel:
         ell = (C.c_double * self.d)(*self.lengthscale.tolist())
         jitter = self.jitter
         for attempt in range(self.max_jitter_tries + 1):
-            spec = _cabi.GpSpec(n=self.n, d=self.d, kernel=self.kernel, reserved=0,
+            spec = _cabi.GpSpec(n=self.n, d=self.d, kernel=self.kernel, reserved=2,   # fp16 planes allowed
                                 sigma_f2=self.variance, sigma_n2=self.noise, jitter=jitter,
                                 X=self.X.data_ptr(), y=self.y.data_ptr(), ell=ell)
             with torch.cuda.device(self.device):
