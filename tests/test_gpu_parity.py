@@ -658,3 +658,26 @@ def test_conditioning_proxy_guards_the_fast_mode():
             assert not [x for x in w if issubclass(x.category, RuntimeWarning)]
             ob.posterior([bad], bad_X[:10], precision="fast")
             assert [x for x in w if issubclass(x.category, RuntimeWarning)]
+
+
+def test_fast_mode_operand_format_follows_conditioning():
+    """K3 stores bf16 planes for well-conditioned GPs and scaled fp16 planes (+ direct-difference distances) beyond
+    kappa = 100; both kernel instantiations meet the tolerance inside the guarded range."""
+    if not _cabi.fast_path_available():
+        pytest.skip("fast path not built")
+    rng = np.random.default_rng(5)
+    seen = set()
+    for n, d, ell in ((600, 10, 0.7), (600, 6, 0.6), (1024, 5, 0.5), (700, 10, 1.5)):
+        X = rng.random((n, d))
+        y = np.sin(3 * X.sum(1))
+        gp = ob.GPModel(X, y, ell * np.ones(d), 1.5, device=DEV)
+        assert gp._flags == (2 if gp.conditioning > 100.0 else 0)
+        seen.add(gp._flags)
+        assert gp.conditioning < ob.GPModel.FAST_MODE_CONDITIONING_LIMIT
+        Xc = rng.random((3000, d))
+        st = O.gp_fit_state(X, y, ell * np.ones(d), 1.5, form="direct")
+        mu_o, var_o = O.gp_posterior(st, Xc)
+        mu, var = ob.posterior([gp], Xc, precision="fast")
+        np.testing.assert_allclose(mu[0].cpu().numpy(), mu_o, rtol=1e-3, atol=1e-3 * max(1.0, np.abs(mu_o).max()))
+        np.testing.assert_allclose(np.sqrt(var[0].cpu().numpy()), np.sqrt(var_o), rtol=1e-3, atol=1e-3 * np.sqrt(1.5))
+    assert seen == {0, 2}
