@@ -129,3 +129,61 @@ def test_allreduce_best_key_gloo_world2():
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] == out[1] == (0.75, 4)
+
+
+# ------------------------------------------------------------------------------------------
+# TuRBO bookkeeping (turbo.py:119-154, :340-380): trust-region length, batch selection
+# ------------------------------------------------------------------------------------------
+def _turbo_problem():
+    from optimobo_b200.problem import Problem
+
+    class P(Problem):
+        def __init__(self):
+            super().__init__(n_var=3, n_obj=2, xl=np.zeros(3), xu=np.ones(3))
+
+        def _evaluate(self, x, out, *args, **kwargs):
+            out["F"] = [x[:, 0], 1 - x[:, 0] + x[:, 1:].sum(1)]
+    return P()
+
+
+def test_turbo_1_trust_region_and_selection():
+    from optimobo_b200.algorithms import TuRBO_1
+    t = TuRBO_1(_turbo_problem(), batch_size=2, ideal_point=[0, 0], max_point=[1, 3], seed=0)
+    assert t.n_cand == 300 and t.failtol == 2 and t.succtol == 3 and t.length == 0.4
+    # select_candidates: the minimiser of each sample, never the same candidate twice
+    X_cand = np.arange(15, dtype=float).reshape(5, 3) / 15
+    y_cand = np.array([[3.0, 3.0], [1.0, 1.0], [2.0, 0.5], [5.0, 5.0], [4.0, 4.0]]).reshape(5, 1, 2)
+    picked = t.select_candidates(X_cand, y_cand.copy())
+    np.testing.assert_array_equal(picked, X_cand[[1, 2]])
+    y_same = np.array([[1.0, 1.0], [2.0, 2.0], [3.0, 3.0], [4.0, 4.0], [5.0, 5.0]]).reshape(5, 1, 2)
+    np.testing.assert_array_equal(t.select_candidates(X_cand, y_same.copy()), X_cand[[0, 1]])
+    # _adjust_length: three successes double the region (capped), `failtol` failures halve it
+    t._restart()
+    t._aggregated_samples = np.array([[1.0]])
+    for _ in range(3):
+        t._adjust_length(np.array([0.5]))
+    assert t.length == 0.8 and t.succcount == 0
+    t._adjust_length(np.array([2.0])); t._adjust_length(np.array([2.0]))
+    assert t.length == 0.4 and t.failcount == 0
+    t._adjust_length(np.array([0.9995]))                 # within 1e-3 relative of the best: a failure
+    assert t.failcount == 1
+    np.testing.assert_allclose(t.denormalise(t.normalise(np.array([[0.2, 0.4, 0.9]]))), [[0.2, 0.4, 0.9]])
+
+
+def test_turbo_m_selection_across_regions():
+    from optimobo_b200.algorithms import TuRBO_M
+    t = TuRBO_M(_turbo_problem(), [0, 0], [1, 3], batch_size=2, n_trust_regions=2, seed=0)
+    assert t.failtol == 5 and t.length.shape == (2,)
+    t.n_cand = 3
+    X_cand = np.arange(18, dtype=float).reshape(2, 3, 3) / 18
+    y_cand = np.array([[[5.0, 0.1], [4.0, 9.0], [3.0, 9.0]], [[0.2, 9.0], [6.0, 9.0], [7.0, 0.05]]])
+    X_next, idx = t._select_candidates(X_cand, y_cand.copy())
+    np.testing.assert_array_equal(X_next, np.stack([X_cand[1, 0], X_cand[1, 2]]))
+    np.testing.assert_array_equal(idx[:, 0], [1, 1])
+    # a region's length reacts to the samples IT proposed (objective 0 of its own history, turbo.py:348)
+    t.ysample = np.array([[1.0, 0.0], [2.0, 0.0], [0.3, 0.0]])
+    t._idx = np.array([[0], [0], [1]])
+    t._adjust_length(np.array([0.5]), 0)
+    assert t.succcount[0] == 1 and t.failcount[0] == 0
+    t._adjust_length(np.array([0.31, 0.4]), 1)
+    assert t.succcount[1] == 0 and t.failcount[1] == 2
