@@ -588,6 +588,175 @@ k_posterior_fast(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
 }
 
 
+// =================================================================================================
+// Mean-only pass (the acquisition never reads this model's variance: model 1.. of EHVI / decomposition in the
+// reference's semantics, the Pareto-label GP of KEEP).  No tensor core, no operand ring: K1 + the dot product with
+// sigma_f2 alpha.  The generator code of the main kernel would leave half of the SM idle here (8 of its 16 warps),
+// so this is a separate 256-thread kernel with a few KB of shared memory: two CTAs per SM, 16 K1 warps.
+// Warp q owns training points 8q..8q+7 of every 64-block, lane l the candidate rows l + 32 rr (as in the main kernel).
+// =================================================================================================
+template <int DP, int R, bool DIRECT>
+__global__ void __launch_bounds__(256, 2)
+k_posterior_mean_fast(const FastParams prm) {
+  constexpr int RB = 128 / (32 * R);
+  constexpr int XT_STRIDE = (DP + 2) * FK;
+  __shared__ float xc[DP * FM];
+  __shared__ __align__(16) float xt[2 * XT_STRIDE];
+  __shared__ float mu_sm[8 * FM];
+  __shared__ double inv_ell[DP];
+  const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
+  const int d = prm.gp.d, np = prm.gp.n_pad, nkb = np / FK;
+  const bool matern = (prm.gp.kernel == OMBO_KERNEL_MATERN52);
+  const long long n_tiles = (prm.m + FM - 1) / FM;
+  if (tid < DP) inv_ell[tid] = tid < d ? 1.0 / prm.gp.ell[tid] : 0.0;
+  constexpr int LD_ROWS = 256 / 16;
+  const int ld_j = tid >> 4, ld_o = (tid & 15) * 4;
+  constexpr int LD_SWEEPS = (DP + 2 + LD_ROWS - 1) / LD_ROWS;
+  auto prefetch_slice = [&](float *dst, int kb) {
+#pragma unroll
+    for (int sw = 0; sw < LD_SWEEPS; ++sw) {
+      const int jj = ld_j + LD_ROWS * sw;
+      if (jj <= DP + 1) {
+        const float *src = (jj < DP) ? prm.gp.xs32 + (size_t)jj * np + kb * FK + ld_o
+                                     : (jj == DP ? prm.gp.alpha32 : prm.gp.b2_32) + kb * FK + ld_o;
+        const uint32_t sd = smem_u32(dst + jj * FK + ld_o);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(sd), "l"(src) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  int xbuf = 0;
+  prefetch_slice(xt, 0);
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    __syncthreads();
+    for (int e = tid; e < FM * DP; e += 256) {
+      const int r_ = e & (FM - 1), j = e >> 7;
+      const long long cg = tile * FM + r_;
+      xc[j * FM + r_] = (cg < prm.m && j < d)
+                            ? -2.0f * (float)((ombo_pool_coord(prm.pool, cg, j) - prm.gp.center[j]) * inv_ell[j])
+                            : 0.f;
+    }
+    __syncthreads();
+    float mu_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float x[R][DP], a2[R];
+    auto load_rows = [&](int rb) {
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < DP; ++j) { x[rr][j] = xc[j * FM + lane + 32 * (R * rb + rr)]; acc = fmaf(x[rr][j], x[rr][j], acc); }
+        a2[rr] = 0.25f * acc;
+      }
+    };
+    if (RB == 1) load_rows(0);
+    for (int kb = 0; kb < nkb; ++kb) {
+      prefetch_slice(xt + (xbuf ^ 1) * XT_STRIDE, (kb + 1 < nkb) ? kb + 1 : 0);
+      const float *xs = xt + xbuf * XT_STRIDE + 8 * q;
+#pragma unroll 1
+      for (int rb = 0; rb < RB; ++rb) {
+        if (RB > 1) load_rows(rb);
+        float2 r2[R][4];
+        if (DIRECT) {
+#pragma unroll
+          for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) r2[rr][e] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < DP; ++j) {
+            const float4 t0 = *(const float4 *)(xs + j * FK);
+            const float4 t1 = *(const float4 *)(xs + j * FK + 4);
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+              const float2 xx = make_float2(x[rr][j], x[rr][j]), hh = make_float2(0.5f, 0.5f);
+              const float2 d0 = __ffma2_rn(xx, hh, make_float2(t0.x, t0.y)), d1 = __ffma2_rn(xx, hh, make_float2(t0.z, t0.w));
+              const float2 d2 = __ffma2_rn(xx, hh, make_float2(t1.x, t1.y)), d3 = __ffma2_rn(xx, hh, make_float2(t1.z, t1.w));
+              r2[rr][0] = __ffma2_rn(d0, d0, r2[rr][0]);
+              r2[rr][1] = __ffma2_rn(d1, d1, r2[rr][1]);
+              r2[rr][2] = __ffma2_rn(d2, d2, r2[rr][2]);
+              r2[rr][3] = __ffma2_rn(d3, d3, r2[rr][3]);
+            }
+          }
+        } else {
+          const float4 n0 = *(const float4 *)(xs + (DP + 1) * FK);
+          const float4 n1 = *(const float4 *)(xs + (DP + 1) * FK + 4);
+#pragma unroll
+          for (int rr = 0; rr < R; ++rr) {
+            const float2 aa = make_float2(a2[rr], a2[rr]);
+            r2[rr][0] = __fadd2_rn(aa, make_float2(n0.x, n0.y));
+            r2[rr][1] = __fadd2_rn(aa, make_float2(n0.z, n0.w));
+            r2[rr][2] = __fadd2_rn(aa, make_float2(n1.x, n1.y));
+            r2[rr][3] = __fadd2_rn(aa, make_float2(n1.z, n1.w));
+          }
+#pragma unroll
+          for (int j = 0; j < DP; ++j) {
+            const float4 t0 = *(const float4 *)(xs + j * FK);
+            const float4 t1 = *(const float4 *)(xs + j * FK + 4);
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+              const float2 xx = make_float2(x[rr][j], x[rr][j]);
+              r2[rr][0] = __ffma2_rn(xx, make_float2(t0.x, t0.y), r2[rr][0]);
+              r2[rr][1] = __ffma2_rn(xx, make_float2(t0.z, t0.w), r2[rr][1]);
+              r2[rr][2] = __ffma2_rn(xx, make_float2(t1.x, t1.y), r2[rr][2]);
+              r2[rr][3] = __ffma2_rn(xx, make_float2(t1.z, t1.w), r2[rr][3]);
+            }
+          }
+        }
+        const float4 al0 = *(const float4 *)(xs + DP * FK);
+        const float4 al1 = *(const float4 *)(xs + DP * FK + 4);
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+          float2 kv[4];
+          if (matern) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 rad, ex;
+              asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad.x) : "f"(fabsf(r2[rr][e].x)));
+              asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad.y) : "f"(fabsf(r2[rr][e].y)));
+              const float2 arg = __fmul2_rn(rad, make_float2(-3.2259955597f, -3.2259955597f));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.x) : "f"(arg.x));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.y) : "f"(arg.y));
+              const float2 poly = __ffma2_rn(rad, make_float2(2.2360679775f, 2.2360679775f),
+                                             __ffma2_rn(r2[rr][e], make_float2(1.6666666667f, 1.6666666667f),
+                                                        make_float2(1.0f, 1.0f)));
+              kv[e] = __fmul2_rn(poly, ex);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 arg = __fmul2_rn(r2[rr][e], make_float2(-0.7213475204f, -0.7213475204f));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(kv[e].x) : "f"(arg.x));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(kv[e].y) : "f"(arg.y));
+            }
+          }
+          float2 m2 = __fmul2_rn(kv[0], make_float2(al0.x, al0.y));
+          m2 = __ffma2_rn(kv[1], make_float2(al0.z, al0.w), m2);
+          m2 = __ffma2_rn(kv[2], make_float2(al1.x, al1.y), m2);
+          m2 = __ffma2_rn(kv[3], make_float2(al1.z, al1.w), m2);
+          const float ms = m2.x + m2.y;
+          if (RB == 1 || rb == 0) mu_acc[rr] += ms; else mu_acc[(R + rr) & 3] += ms;
+        }
+      }
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+      __syncthreads();
+      xbuf ^= 1;
+    }
+#pragma unroll
+    for (int r4 = 0; r4 < 4; ++r4) mu_sm[q * FM + lane + 32 * r4] = mu_acc[r4];
+    __syncthreads();
+    if (tid < FM) {
+      const long long cg = tile * FM + tid;
+      if (cg < prm.m) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) acc += mu_sm[w * FM + tid];
+        prm.mu_out[cg] = (double)acc;
+        prm.var_out[cg] = nan("");
+      }
+    }
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -669,6 +838,28 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
     return OMBO_ERR_UNSUPPORTED;
   }
   long long tiles = (m + FM - 1) / FM;
+  if (!want_var && gp.d <= 12 && !getenv("OMBO_FAST_MEAN_IN_MAIN")) {
+    // mean-only: the dedicated K1 kernel (two CTAs per SM; d <= 12 keeps 4 rows x d coordinates in registers)
+    FastParams prm;
+    prm.gp = gp; prm.pool = pool; prm.m = m; prm.mu_out = mu; prm.var_out = var; prm.mean_only = 1;
+    prm.kcache = nullptr; prm.prof = nullptr; prm.dbg = 0; prm.trim_b = 0;
+    const long long tiles = (m + FM - 1) / FM;
+    const int grid = (int)(tiles < 2LL * ctx->num_sms ? tiles : 2LL * ctx->num_sms);
+    const bool direct = (gp.flags & OMBO_GP_FP16_PLANES) != 0;
+    ProfScope prof(ctx, s);
+#define MEAN_CASE(DPV, RV)                                                                              \
+    if (gp.d <= DPV) {                                                                                  \
+      if (direct) k_posterior_mean_fast<DPV, RV, true><<<grid, 256, 0, s>>>(prm);                       \
+      else k_posterior_mean_fast<DPV, RV, false><<<grid, 256, 0, s>>>(prm);                             \
+    } else
+    MEAN_CASE(2, 4) MEAN_CASE(4, 4) MEAN_CASE(6, 4) MEAN_CASE(8, 4) MEAN_CASE(10, 4)
+    { if (direct) k_posterior_mean_fast<12, 4, true><<<grid, 256, 0, s>>>(prm);
+      else k_posterior_mean_fast<12, 4, false><<<grid, 256, 0, s>>>(prm); }
+#undef MEAN_CASE
+    ctx->launches += 1;
+    OMBO_CUDA(cudaGetLastError());
+    return OMBO_OK;
+  }
   // default: single-CTA UMMA with 256-column chunks (mode 3).  The B200s of this pool run the kernel at their 1 kW
   // power cap (SM clock ~1.6 GHz), where time follows energy, i.e. issued tensor work: the single-CTA variant can
   // shrink N on the diagonal K-blocks, the cta_group::2 variants cannot (N is split across the pair) and issue 17 %
