@@ -109,14 +109,13 @@ class PoolOptimiserBase:
         if self.precision != "auto":
             return self.precision
         from .. import _cabi
-        # small / ill-conditioned GPs: FP64 is cheap and the fast mode's 1e-3 tolerance is not met near
-        # training points (DESIGN.md "fast mode validity")
+        # tiny GPs: FP64 is cheap.  Otherwise the fast mode is used exactly where its accuracy is guaranteed:
+        # d <= 24 and a well-conditioned factor on every model (GPModel.conditioning, scripts/cond_study.py) --
+        # many points per length-scale in few dimensions (README MyProblem: kappa ~ 1e8) run FP64.
         n = max(m.n for m in models)
         d = models[0].d
-        if not (_cabi.fast_path_available() and n > 256 and d <= 24):
+        if not (_cabi.fast_path_available() and n >= 64 and d <= 24):
             return "fp64"
-        # ... and large but ill-conditioned ones (many points per length-scale in few dimensions): the 3-product
-        # split then loses absolute accuracy on sigma (GPModel.conditioning, scripts/cond_study.py)
         from ..gp import GPModel
         return "fast" if max(m.conditioning for m in models) <= GPModel.FAST_MODE_CONDITIONING_LIMIT else "fp64"
 

@@ -652,6 +652,9 @@ def test_conditioning_proxy_guards_the_fast_mode():
     base = PoolOptimiserBase(Problem(n_var=10, n_obj=2, xl=np.zeros(10), xu=np.ones(10)), device=DEV)
     if _cabi.fast_path_available():
         assert base._precision_for([good]) == "fast" and base._precision_for([bad]) == "fp64"
+        mid = ob.GPModel(good_X[:200], y[:200], 0.7 * np.ones(10), 1.5, device=DEV)      # C2-sized: fast as well
+        tiny = ob.GPModel(good_X[:40], y[:40], 0.7 * np.ones(10), 1.5, device=DEV)       # tiny: FP64 is cheap
+        assert base._precision_for([mid]) == "fast" and base._precision_for([tiny]) == "fp64"
         with warnings.catch_warnings(record=True) as w:
             warnings.simplefilter("always")
             ob.posterior([good], good_X[:10], precision="fast")
