@@ -14,4 +14,6 @@ from .acquisition import (  # noqa: F401
     spec_expected_decomposition, spec_hv_poi, spec_pareto_ei,
 )
 
+from . import fit, algorithms  # noqa: F401,E402
+
 __version__ = "0.1.0"
