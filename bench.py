@@ -13,12 +13,17 @@ counter-generated uniform candidate pool of m candidates per GPU per step (weak 
            (chunked, overlapped with scoring) and the 16-byte result is read back.
   roofline: the dominant kernel (posterior: K1+K2) timed with CUDA events on its stream
            inside the timed region (C-ABI profile hooks), algorithmic FLOPs/candidate from
-           SURVEY section 8d.
+           SURVEY section 8d (G_var follows --semantics).
   cpu_baseline: the numpy/LAPACK oracle port (oracle/oracle.py) on the host cores on a
-           bounded sample of the same workload.
-  --impl reference : the same oracle port as the measured arm (the reference is pure Python,
-           cannot travel to the GPU box, and scores one candidate per call; the batched port
-           is its best case).  Rank 0 only.
+           bounded sample of the same workload, plus `reference_call_pattern`: the REFERENCE'S OWN
+           util_functions.EHVI, one candidate per call (the pattern differential_evolution drives),
+           timed on 256 candidates when the reference package is present (baseline/_ref).
+  sweep / strong / fp64 / reference_semantics / accuracy / parity_nranks: sub-records that tell the
+           rest of the C5 story in the same line (pool sizes 2^20..2^26 per GPU, fixed-pool strong
+           scaling at this N, the FP64 tolerance mode with its own DGEMM roofline, the reference's
+           model-0-variance semantics, the measured fast-mode error, and the N-rank result parity).
+  --impl reference : the same oracle port as the measured arm (the reference is pure Python and
+           scores one candidate per call; the batched port is its best case).  Rank 0 only.
 """
 from __future__ import annotations
 
@@ -56,6 +61,12 @@ def workload(n=N_TRAIN, d=DIM):
 def algorithmic_flops_per_candidate(n, d, G, G_var, P):
     """F = G_var n^2 + G (2n + n(3d+10)) + A, A(EHVI-2D) ~ 30 P."""
     return G_var * n * n + G * (2 * n + n * (3 * d + 10)) + 30 * P
+
+
+def issued_units_per_mac(fmt):
+    """Tensor-core products per algorithmic MAC, in units of one 16-bit product: the 16-bit x3 split issues 3, the
+    f8c format 1 (fp16) + 2 x 1/2 (e4m3 at twice the rate)."""
+    return 2.0 if fmt == "f8c" else 3.0
 
 
 class ClockSampler(threading.Thread):
@@ -123,6 +134,43 @@ def cpu_oracle_rate(budget_s, chunk=4096, semantics="exact"):
     return done / el, done, el
 
 
+def reference_call_pattern(n_cand=256):
+    """the reference's own `util_functions.EHVI` (util_functions.py:136-167, EHVI_2D_aux
+    :81-133) called with ONE x per call -- what scipy's differential_evolution does at optimisers.py:118 -- on the
+    C5 workload, with sklearn's GaussianProcessRegressor behind a GPy-shaped predict (GPy is not installable).
+    Needs the reference package (baseline/_ref, /root/reference or $OPTIMOBO_REF); otherwise the figure measured in
+    the build container is reported as such."""
+    from oracle import ref_loader as R
+    from oracle import oracle as O
+    if not R.reference_available():
+        return {"value": 97.8, "unit": "candidates/s", "cores": 8, "measured": "build container (SURVEY probe), "
+                "reference package not present on this box", "candidates": 256}
+    uf = R.load_reference().util_functions
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import ConstantKernel, Matern
+    from scipy.stats import norm, qmc
+    X, Y, ells, sf2 = workload()
+    models = []
+    for i in range(N_OBJ):
+        g = GaussianProcessRegressor(kernel=ConstantKernel(sf2[i]) * Matern(length_scale=ells[i], nu=2.5), alpha=1e-8,
+                                     optimizer=None, normalize_y=False).fit(X, Y[:, i])
+
+        def post(Xq, g=g):
+            mu, sd = g.predict(Xq, return_std=True)
+            return mu, sd * sd
+        models.append(R.ShimGP(post))
+    PF, r = uf.calc_pf(Y), Y.max(0)
+    cache = norm.ppf(qmc.Sobol(d=2, scramble=True, seed=0).random_base2(m=5))
+    Xc = O.candidates_from_counter(1, 0, n_cand, np.zeros(DIM), np.ones(DIM))
+    uf.EHVI(Xc[0], models, r, PF, cache)
+    t0 = time.perf_counter()
+    vals = [float(np.asarray(uf.EHVI(x, models, r, PF, cache)).reshape(-1)[0]) for x in Xc]
+    el = time.perf_counter() - t0
+    return {"value": n_cand / el, "unit": "candidates/s", "cores": os.cpu_count(), "candidates": n_cand,
+            "seconds": el, "measured": "this box: unmodified optimobo.util_functions.EHVI from " + R.reference_root() +
+            ", one x per call, sklearn GPR behind a GPy-shaped predict", "best_value": max(vals)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -149,6 +197,10 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    try:
+        line["cpu_baseline"]["reference_call_pattern"] = reference_call_pattern()
+    except Exception as e:          # the batched port above is the measured arm; this is the extra baseline
+        line["cpu_baseline"]["reference_call_pattern"] = {"error": repr(e)}
     print(json.dumps(line))
 
 
@@ -165,6 +217,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fit", action="store_true", help="skip the (untimed, separately reported) device hyper-parameter fit")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sweep / strong / fp64 / reference-semantics / accuracy sub-records")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -231,17 +284,45 @@ def main():
     cache = ob.host_prep.cached_samples(2, 5, seed=0)
     PF, r = ob.host_prep.calc_pf(Y), Y.max(0)
     spec = ob.spec_ehvi(r, PF, cache, args.semantics)
-    pool = ob.CandidatePool.counter(m_total, np.zeros(DIM), np.ones(DIM), seed=1)
     ctx = _cabi.Context.get(local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-
-    def step():
-        return score_sharded(models, spec, pool, precision=precision, rescoring=(world > 1))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed(step, steps, warmup, profile=False):
+        """W untimed + K timed steps of `step` (L2 flushed between steps, outside the events), barrier +
+        synchronize on both sides, CUDA events per step, MAX over ranks.  -> (total ms, last result, n_prof, prof_ms)"""
+        for _ in range(warmup):
+            flush.zero_()
+            step()
+        barrier()
+        if profile:
+            ctx.profile(True)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        result = None
+        for i in range(steps):
+            flush.zero_()
+            starts[i].record()
+            result = step()
+            ends[i].record()
+        barrier()
+        n_prof, prof_ms = ctx.profile_read() if profile else (0, 0.0)
+        if profile:
+            ctx.profile(False)
+        t = torch.tensor([sum(s.elapsed_time(e) for s, e in zip(starts, ends))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), result, n_prof, prof_ms
+
+    # ---- headline: C5, 2^log2m candidates per GPU per step --------------------------------------
+    pool = ob.CandidatePool.counter(m_total, np.zeros(DIM), np.ones(DIM), seed=1)
+
+    def step():
+        return score_sharded(models, spec, pool, precision=precision)
 
     for _ in range(args.warmup):
         flush.zero_()
@@ -251,27 +332,11 @@ def main():
     if sampler:
         sampler.start()
     ctx.launch_count(reset=True)
-    ctx.profile(True)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     wall0 = time.perf_counter()
-    result = None
-    for i in range(args.steps):
-        flush.zero_()                      # L2 flush between timed iterations (outside the events)
-        starts[i].record()
-        result = step()
-        ends[i].record()
-    barrier()
+    total_ms, result, n_prof, prof_ms = timed(step, args.steps, 0, profile=True)
     wall = time.perf_counter() - wall0
-    n_prof, prof_ms = ctx.profile_read()
-    ctx.profile(False)
     launches = ctx.launch_count(reset=True)
     clocks = sampler.summary() if sampler else None
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    t = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
     value = m_total * args.steps / (total_ms / 1e3)
 
     # ---- end-to-end: host candidates through the C-ABI host entry ------------------------------
@@ -298,6 +363,121 @@ def main():
                "h2d_bytes_per_step": int(Xh.numel() * Xh.element_size()), "d2h_bytes_per_step": 16,
                "steps": k_e2e, "host_dtype": str(host_dtype).replace("torch.", ""),
                "wall_s": time.perf_counter() - w0}
+        del Xh
+
+    # ---- N-rank result parity (outside the timed region): the sharded winner == the single-GPU winner ----------
+    parity_nranks = None
+    if world > 1:
+        ppool = ob.CandidatePool.counter(1 << 22, np.zeros(DIM), np.ones(DIM), seed=7)
+        v_sh, i_sh = score_sharded(models, spec, ppool, precision=precision)
+        whole = ob.score(models, spec, ppool, precision=precision)           # every rank: the whole pool on one GPU
+        ok = (i_sh == whole.best_index) and (v_sh == whole.best_value)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity_nranks = "ok" if int(flag.item()) == 1 else f"MISMATCH sharded=({v_sh}, {i_sh}) single=({whole.best_value}, {whole.best_index})"
+        if parity_nranks != "ok":
+            raise SystemExit("N-rank parity failed: " + parity_nranks)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    n, d, P = N_TRAIN, DIM, len(PF)
+    bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    bf16_src = ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+                if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)")
+    dgemm = {}
+
+    def dgemm_peak():
+        """no FP64 peak in MEASURED_PEAKS.json: cuBLAS DGEMM measured in this run"""
+        if "v" not in dgemm:
+            a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+            b = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+            best = 1e9
+            for _ in range(6):
+                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_.record(); torch.matmul(a, b); e_.record(); torch.cuda.synchronize()
+                best = min(best, s_.elapsed_time(e_))
+            dgemm["v"] = 2 * 4096 ** 3 / (best / 1e3) / 1e12
+        return dgemm["v"]
+
+    def roofline_of(prec, semantics, m_gpu, steps, n_prof_, prof_ms_, tot_ms):
+        """Roofline of the posterior kernel (K1 + K2): algorithmic FLOPs from SURVEY section 8d with G_var taken from
+        the semantics (reference semantics reads only model 0's variance), over the CUDA-event time of its launches."""
+        G_var = N_OBJ if semantics == "exact" else 1
+        fl_cand = algorithmic_flops_per_candidate(n, d, N_OBJ, G_var, P)
+        if prec == "fast":
+            peak, src = bf16_peak, bf16_src
+        else:
+            peak, src = dgemm_peak(), "cuBLAS DGEMM 4096^3 measured in this run (best of 6)"
+        launch_ms = prof_ms_ / max(1, n_prof_)
+        # the profiled launches are the posterior kernels of all GPs; their algorithmic work per candidate is F - A
+        fl_total = (fl_cand - 30 * P) * m_gpu * steps
+        achieved = fl_total / (prof_ms_ / 1e3) / 1e12 if n_prof_ else None
+        return {"bound": "tensor", "kernel": "k_posterior_" + ("fast" if prec == "fast" else "fp64"),
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                "peak_source": src, "launches": n_prof_, "avg_launch_ms": launch_ms,
+                "candidates_per_launch": m_gpu * steps * N_OBJ / max(1, n_prof_),
+                "kernel_share_of_step": prof_ms_ / tot_ms if tot_ms else None, "flops_per_candidate": fl_cand,
+                "g_var": G_var}
+
+    # ---- sub-records: pool-size sweep, strong scaling, FP64 mode, reference semantics, accuracy ---------------
+    extras = {}
+    if not args.no_extras:
+        def run_pool(m_tot, prec, sem, steps, warmup, profile=False):
+            p_ = ob.CandidatePool.counter(m_tot, np.zeros(DIM), np.ones(DIM), seed=1)
+            sp_ = spec if sem == args.semantics else ob.spec_ehvi(r, PF, cache, sem)
+            tot, res, npf, pms = timed(lambda: score_sharded(models, sp_, p_, precision=prec), steps, warmup, profile)
+            return {"candidates_total": m_tot, "candidates_per_gpu": m_tot // world, "steps": steps,
+                    "ms_per_step": tot / steps, "value": m_tot * steps / (tot / 1e3), "best": list(res)}, npf, pms, tot
+
+        if precision == "fast":
+            sweep = []
+            for lg in (20, 22, 24, 26):
+                st_ = 2 if lg == 26 else 3
+                rec, _, _, _ = run_pool((1 << lg) * world, "fast", args.semantics, st_, 1)
+                rec["log2m_per_gpu"] = lg
+                sweep.append(rec)
+            extras["sweep"] = {"scaling": "weak", "unit": "candidates/s", "precision": "fast", "semantics": args.semantics,
+                               "points": sweep}
+            strong = []
+            for lg in (24, 26):
+                st_ = 2 if lg == 26 else 3
+                rec, _, _, _ = run_pool(1 << lg, "fast", args.semantics, st_, 1)
+                rec["log2m_total"] = lg
+                strong.append(rec)
+            extras["strong"] = {"scaling": "strong", "unit": "candidates/s", "n_gpus": world, "precision": "fast",
+                                "note": "fixed total pool sharded over the run's N GPUs (includes refresh-free scoring, the "
+                                        "16-byte all-gather and the readback)", "points": strong}
+            rec, npf, pms, tot = run_pool((1 << 24) * world, "fast", "reference" if args.semantics == "exact" else "exact", 3, 1, True)
+            other = "reference" if args.semantics == "exact" else "exact"
+            rec["roofline"] = roofline_of("fast", other, 1 << 24, 3, npf, pms, tot)
+            rec["note"] = ("reference semantics: EHVI scales both objectives by MODEL 0's variance (util_functions.py:233), so only "
+                           "model 0 runs K2; model 1 runs the mean-only kernel" if other == "reference" else "exact semantics")
+            extras[other + "_semantics"] = rec
+        if precision == "fast":
+            rec, npf, pms, tot = run_pool((1 << 20) * world, "fp64", args.semantics, 3, 1, True)
+            rec["roofline"] = roofline_of("fp64", args.semantics, 1 << 20, 3, npf, pms, tot)
+            extras["fp64"] = rec
+        if precision == "fast" and rank == 0:
+            # measured error of the fast mode against the FP64 CUDA path on the head of the same pool (2^16 candidates)
+            hp = ob.CandidatePool.counter(1 << 16, np.zeros(DIM), np.ones(DIM), seed=1)
+            f_ = ob.score(models, spec, hp, precision="fast", want_posterior=True, want_acq=True)
+            q_ = ob.score(models, spec, hp, precision="fp64", want_posterior=True, want_acq=True)
+            sf, sq = f_.var.sqrt(), q_.var.sqrt()
+            af, aq = f_.acq, q_.acq
+            amax = float(aq.abs().max())
+            sel = aq.abs() > 1e-3 * amax
+            extras["accuracy"] = {
+                "sample": "first 2^16 candidates of the pool, fast vs FP64 CUDA path (FP64 path vs sklearn / oracle: tests)",
+                "sigma_max_rel_err": float(((sf - sq).abs() / sq).max()),
+                "sigma_max_abs_err_over_sigma_f": float(((sf - sq).abs() / torch.tensor(sf2, device=dev).sqrt()[:, None]).max()),
+                "mu_max_abs_err_over_sigma": float(((f_.mu - q_.mu).abs() / sq).max()),
+                "ehvi_max_rel_err_where_above_1e-3_of_max": float(((af - aq).abs()[sel] / aq.abs()[sel]).max()),
+                "ehvi_max_abs_err_over_max": float((af - aq).abs().max() / amax),
+                "same_argmax": bool(f_.best_index == q_.best_index),
+                "plane_format": [g.plane_format for g in models], "conditioning": [g.conditioning for g in models]}
 
     if rank != 0:
         if world > 1:
@@ -305,56 +485,26 @@ def main():
         return
 
     # ---- roofline of the dominant kernel ---------------------------------------------------
-    n, d, P = N_TRAIN, DIM, len(PF)
-    fl_cand = algorithmic_flops_per_candidate(n, d, N_OBJ, N_OBJ, P)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    if precision == "fast":
-        peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak_src = ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
-                    if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)")
-    else:
-        # no FP64 peak in MEASURED_PEAKS.json: measure cuBLAS DGEMM here
-        a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
-        b = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
-        best = 1e9
-        for _ in range(6):
-            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s_.record(); torch.matmul(a, b); e_.record(); torch.cuda.synchronize()
-            best = min(best, s_.elapsed_time(e_))
-        peak = 2 * 4096 ** 3 / (best / 1e3) / 1e12
-        peak_src = "cuBLAS DGEMM 4096^3 measured in this run (best of 6)"
-    launch_ms = prof_ms / max(1, n_prof)
-    # one posterior launch covers ONE GP for one chunk of <= 2^20 candidates: its algorithmic share is
-    # (F - A) / G per candidate (the acquisition term A belongs to k_acquire)
-    cand_per_launch = m_per_gpu * args.steps * N_OBJ / max(1, n_prof)
-    fl_launch = (fl_cand - 30 * P) / N_OBJ * cand_per_launch
-    achieved = fl_launch / (launch_ms / 1e3) / 1e12 if n_prof else None
+    roofline = roofline_of(precision, args.semantics, m_per_gpu, args.steps, n_prof, prof_ms, total_ms)
     traffic = None
     try:   # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the same size (ncu --set full capture)
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[precision]
     except Exception:
         pass
-    roofline = {"bound": "tensor", "kernel": "k_posterior_" + ("fast" if precision == "fast" else "fp64"),
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                "peak_source": peak_src, "launches": n_prof, "avg_launch_ms": launch_ms,
-                "candidates_per_launch": cand_per_launch,
-                "kernel_share_of_step": prof_ms / total_ms if total_ms else None,
-                "flops_per_candidate": fl_cand}
-    if precision == "fast" and achieved:
-        # what the tensor cores actually execute: 3 16-bit products per split-precision MAC, and the 128-wide
-        # diagonal blocks of the triangular factor are multiplied densely (68 of 64 ideal units at n = 1024)
+    roofline["traffic"] = traffic
+    if precision == "fast" and roofline["achieved"]:
+        # what the tensor cores actually execute: products per algorithmic MAC of the operand format in use, and the
+        # diagonal blocks of the triangular factor rounded up to 64 columns (68 of 64 ideal units at n = 1024)
+        fmt = models[0].plane_format
         nch = N_TRAIN // 128
         units = sum(2 * c + 2 for c in range(nch)) - 0.5 * nch
-        issued = 3 * units * (128 * 64) * 2              # FLOP per candidate per GP: units of 128 columns x 64 K
-        issued_tflops = issued * cand_per_launch / (launch_ms / 1e3) / 1e12
-        roofline["issued"] = {"tflops": issued_tflops, "frac": issued_tflops / peak,
-                              "note": "bf16x3 split (fp16x3 planes for ill-conditioned GPs): 3 tensor-core products per algorithmic MAC, "
-                                      "diagonal blocks dense; this is the tensor-pipe work the kernel sustains"}
+        issued = issued_units_per_mac(fmt) * units * (128 * 64) * 2      # FLOP-equivalents per candidate per GP
+        G_var = roofline["g_var"]
+        issued_tflops = issued * G_var * m_per_gpu * args.steps / (prof_ms / 1e3) / 1e12
+        roofline["issued"] = {"tflops_bf16_equivalent": issued_tflops, "frac": issued_tflops / roofline["peak"],
+                              "units_per_mac": issued_units_per_mac(fmt), "plane_format": fmt,
+                              "note": "tensor-pipe work the kernel sustains, in units of one 16-bit product per MAC (an e4m3 "
+                                      "product counts 1/2: twice the rate); includes the mean-only launches' time when G_var < G"}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -362,17 +512,22 @@ def main():
         cpu = {"value": rate, "unit": "candidates/s", "cores": os.cpu_count(), "kind": "port",
                "sample": f"{done} candidates of the same pool in {el:.1f} s: batched numpy/LAPACK oracle "
                          "(FP64 posterior x2 + vectorised EHVI, 4096-row chunks), all BLAS threads"}
+        try:
+            cpu["reference_call_pattern"] = reference_call_pattern()
+        except Exception as e:
+            cpu["reference_call_pattern"] = {"error": repr(e)}
 
+    fmt0 = models[0].plane_format
     line = {
         "metric": "candidates scored/sec (GP mean+std+EHVI)", "value": value, "unit": "candidates/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16x3" if precision == "fast" else "f64", "data": "synthetic",
+        "dtype": ("fp16+2xe4m3" if fmt0 == "f8c" else fmt0) if precision == "fast" else "f64", "data": "synthetic",
         "config": {"workload": f"C5: n_train={n} d={d} k=2, full posterior + EHVI-2D ({args.semantics} semantics) + arg-max",
                    "candidates_per_gpu_per_step": m_per_gpu, "precision": precision,
                    "l2": "256 MB flush between timed iterations",
                    "pool": "counter-generated on device (value) / pinned host buffer (e2e)",
-                   "parallelism": f"dp{world} (pool sharded, GP state replicated)"},
+                   "parallelism": f"dp{world} (pool sharded, GP state replicated, one 16-byte all-gather)"},
         "ms_per_bo_iter": {"gp_refresh_x2": refresh_ms, "score_and_reduce": total_ms / args.steps,
                            "first_refresh_incl_init": refresh_first_ms,
                            "hyperparameter_fit_40_evals_one_gp": fit_ms,
@@ -380,6 +535,9 @@ def main():
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "best": {"value": result[0], "index": result[1]}, "wall_s_timed_region": wall,
     }
+    if parity_nranks is not None:
+        line["parity_nranks"] = parity_nranks
+    line.update(extras)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -131,6 +131,11 @@ int ombo_gp_nlml_grad(ombo_ctx *ctx, const ombo_gp_spec *spec, void *state, doub
  * was asked for them (ombo_gp_spec.reserved bit 1 set): a caller that leaves both `reserved` fields 0 always
  * gets, and scores with, bf16 planes. */
 #define OMBO_GP_FP16_PLANES 2
+/* Third format, "f8c" (status word 1 = 2, bit 2 of `reserved`): hi plane fp16, lo field = two e4m3 planes
+ * (e4m3(2^-12 B) and e4m3(B - fp16(B))) for the pair kernel that runs one fp16 product plus two e4m3 correction
+ * products (2.0 tensor units per MAC instead of 3.0).  Chosen only when the refresh was asked for it (spec bit 2),
+ * d <= 12 and the conditioning proxy is below the measured limit. */
+#define OMBO_GP_F8C_PLANES 4
 typedef struct {
   int32_t n, d, kernel, reserved;
   double sigma_f2, sigma_n2;
@@ -183,6 +188,12 @@ int ombo_score(ombo_ctx *ctx, const ombo_gp *gps, int n_gp, const ombo_pool *poo
  * call returns after the result is on the host. */
 int ombo_score_host(ombo_ctx *ctx, const ombo_gp *gps, int n_gp, const ombo_pool *pool,
                     const ombo_acq *acq, int precision, ombo_best *best_host, void *stream);
+
+/* The device scalarisation switch on explicit objective vectors: out[r] = g(F[r, :], weights) with F DEVICE (m, n_obj)
+ * row-major f64 and the function / bounds / weights / parameters taken from `acq` (scalarisation, n_obj, ideal, maxp,
+ * weights, sc_params).  Device twin of `Scalarisation.__call__(F, weights)` (optimobo/scalarisations.py:20-27, the
+ * twelve `_do` at :43,66,92,130,165,190,212,230,257,291,325,375); checked against the reference-minted fixtures. */
+int ombo_scalarise(ombo_ctx *ctx, const ombo_acq *acq, const double *F, int64_t m, double *out, void *stream);
 
 /* K4+K5 alone on caller-supplied posteriors: mu/var DEVICE (n_gp, ld) f64, m <= ld candidates.
  * Lets the acquisition arithmetic be checked against fixtures independently of the GP path. */

@@ -9,8 +9,9 @@ from .gp import GPModel  # noqa: F401
 from .acquisition import (  # noqa: F401
     AcquisitionSpec, CandidatePool, EHVI, EHVI_3D, acquire_from_posterior, consraint_ei, evaluate,
     expected_decomposition,
-    expected_improvement, hypervolume_based_PoI, pareto_expected_improvement, posterior, propose,
-    propose_host, score, spec_constrained_ei, spec_ehvi, spec_ehvi3d, spec_ei,
+    expected_improvement, hypervolume_based_PoI, pareto_expected_improvement, polish, posterior, propose,
+    top_candidates,
+    propose_host, resolve_precision, scalarise_on_device, score, spec_constrained_ei, spec_ehvi, spec_ehvi3d, spec_ei,
     spec_expected_decomposition, spec_hv_poi, spec_pareto_ei,
 )
 

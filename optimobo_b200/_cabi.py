@@ -27,7 +27,7 @@ EXPORTS = [
     "ombo_gp_state_bytes", "ombo_gp_state_field", "ombo_gp_refresh", "ombo_gp_nlml_grad", "ombo_score",
     "ombo_score_host", "ombo_acquire_posterior", "ombo_pool_rows", "ombo_launch_count",
     "ombo_pack_key", "ombo_profile_enable", "ombo_profile_read",
-    "ombo_pareto_mask", "ombo_hypervolume", "ombo_cells_2d", "ombo_posterior_joint_samples",
+    "ombo_pareto_mask", "ombo_hypervolume", "ombo_cells_2d", "ombo_posterior_joint_samples", "ombo_scalarise",
 ]
 
 
@@ -103,6 +103,7 @@ def lib():
                                   C.c_int, C.POINTER(Best), C.c_void_p]
     L.ombo_acquire_posterior.argtypes = [C.c_void_p, C.POINTER(Acq), C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                          C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ombo_scalarise.argtypes = [C.c_void_p, C.POINTER(Acq), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     L.ombo_pool_rows.argtypes = [C.c_void_p, C.POINTER(Pool), C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
     L.ombo_pack_key.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ombo_pareto_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]

@@ -24,9 +24,32 @@ import numpy as np
 import torch
 
 from . import _cabi, host_prep
-from .gp import GPModel, current_stream_ptr
+from .gp import GPModel, _as_device, current_stream_ptr
 
 _PREC = {"fp64": _cabi.PREC_FP64, "fast": _cabi.PREC_FAST}
+
+
+def resolve_precision(models, precision):
+    """'fp64' | 'fast' | 'auto' -> 'fp64' | 'fast'.  'auto' picks the fast mode exactly where its accuracy is
+    guaranteed: the tcgen05 path is built, n >= 64 (tiny GPs are cheap in FP64), d <= 24 and the conditioning
+    proxy of EVERY model is below GPModel.FAST_MODE_CONDITIONING_LIMIT (scripts/cond_study.py); many points per
+    length-scale in few dimensions (README MyProblem: kappa ~ 1e8) run FP64.  An explicit 'fast' on an
+    ill-conditioned GP is honoured with a RuntimeWarning."""
+    models = [models] if isinstance(models, GPModel) else list(models)
+    if precision == "auto":
+        n = max(m.n for m in models)
+        if not (_cabi.fast_path_available() and n >= 64 and models[0].d <= 24):
+            return "fp64"
+        return "fast" if max(m.conditioning for m in models) <= GPModel.FAST_MODE_CONDITIONING_LIMIT else "fp64"
+    if precision not in _PREC:
+        raise ValueError(f"precision must be 'fp64', 'fast' or 'auto' (got {precision!r})")
+    if precision == "fast":
+        worst = max(m.conditioning for m in models)
+        if worst > GPModel.FAST_MODE_CONDITIONING_LIMIT:
+            warnings.warn(f"fast precision on an ill-conditioned GP (conditioning proxy {worst:.1e} > "
+                          f"{GPModel.FAST_MODE_CONDITIONING_LIMIT:.0e}): sigma may be off by more than 1e-3 sigma_f; "
+                          "use precision='fp64' or 'auto'", RuntimeWarning, stacklevel=3)
+    return precision
 _SEM = {"reference": _cabi.SEM_REFERENCE, "exact": _cabi.SEM_EXACT}
 
 
@@ -95,9 +118,9 @@ class CandidatePool:
         if self.X is not None:
             i = index - self.index_base
             return self.X[i:i + count].double()
-        dev = torch.device(device if device is not None else "cuda:0")
+        dev = _as_device(device)
         out = torch.empty((count, self.d), dtype=torch.float64, device=dev)
-        ctx = _cabi.Context.get(dev.index or 0)
+        ctx = _cabi.Context.get(dev.index)
         p = self.c_struct()
         with torch.cuda.device(dev):
             _cabi.check(_cabi.lib().ombo_pool_rows(ctx.handle, C.byref(p), index, count,
@@ -253,12 +276,7 @@ def score(models, spec, pool, precision="fp64", want_posterior=False, want_acq=F
             raise ValueError("all models must live on the same device")
     if pool.X is not None and pool.X.device != dev:
         raise ValueError("pool and models are on different devices")
-    if precision == "fast":
-        worst = max(mdl.conditioning for mdl in models)
-        if worst > GPModel.FAST_MODE_CONDITIONING_LIMIT:
-            warnings.warn(f"fast precision on an ill-conditioned GP (conditioning proxy {worst:.1e} > "
-                          f"{GPModel.FAST_MODE_CONDITIONING_LIMIT:.0e}): sigma may be off by more than 1e-3 sigma_f; "
-                          "use precision='fp64' or 'auto'", RuntimeWarning, stacklevel=2)
+    precision = resolve_precision(models, precision)
     G = len(models)
     gps = (_cabi.Gp * G)(*[m.c_struct(var_floor) for m in models])
     p = pool.c_struct()
@@ -294,20 +312,46 @@ def score(models, spec, pool, precision="fp64", want_posterior=False, want_acq=F
 def acquire_from_posterior(spec, mu, var, device="cuda:0", index_base=0):
     """K4+K5 on caller-supplied posteriors mu/var (n_models, m): returns (acq (m,) CUDA tensor,
     best_value, best_index)."""
-    dev = torch.device(device)
+    dev = _as_device(device)
     mu_t = torch.as_tensor(np.ascontiguousarray(np.atleast_2d(np.asarray(mu, dtype=np.float64)))).to(dev)
     var_t = torch.as_tensor(np.ascontiguousarray(np.atleast_2d(np.asarray(var, dtype=np.float64)))).to(dev)
     G, m = mu_t.shape
     a = spec.c_struct(dev)
     acq = torch.empty((m,), dtype=torch.float64, device=dev)
     best = torch.empty((2,), dtype=torch.int64, device=dev)
-    ctx = _cabi.Context.get(dev.index or 0)
+    ctx = _cabi.Context.get(dev.index)
     with torch.cuda.device(dev):
         _cabi.check(_cabi.lib().ombo_acquire_posterior(
             ctx.handle, C.byref(a), G, C.c_void_p(mu_t.data_ptr()), C.c_void_p(var_t.data_ptr()), m, m,
             index_base, C.c_void_p(acq.data_ptr()), C.c_void_p(best.data_ptr()), current_stream_ptr(dev)))
     host = best.cpu()
     return acq, float(host[:1].view(torch.float64)[0]), int(host[1])
+
+
+def scalarise_on_device(agg_func, F, weights, device="cuda:0"):
+    """g(F[r, :], weights) for every row of F (m, k) through the CUDA scalarisation switch -- the device twin of
+    `agg_func(F, weights)` (scalarisations.py:20-27).  `agg_func` is a scalarisation object of this package or of
+    the reference (adopted by class name); returns a (m,) numpy array."""
+    dev = _as_device(device)
+    if not hasattr(agg_func, "device_spec"):
+        agg_func = adopt_scalarisation(agg_func)
+    Fh = np.ascontiguousarray(np.atleast_2d(np.asarray(F, dtype=np.float64)))
+    m, k = Fh.shape
+    if k > _cabi.MAX_OBJ:
+        raise ValueError(f"the device scalarisation switch takes up to {_cabi.MAX_OBJ} objectives (got {k})")
+    sc_id, params = agg_func.device_spec()
+    spec = AcquisitionSpec(kind=_cabi.ACQ_EXPECTED_DECOMP, n_obj=k, scalarisation=sc_id, sc_params=params,
+                           ideal=tuple(np.asarray(agg_func.ideal_point, float)),
+                           maxp=tuple(np.asarray(agg_func.max_point, float)),
+                           weights=tuple(np.asarray(weights, float).reshape(-1)))
+    a = spec.c_struct(dev)
+    Fd = torch.as_tensor(Fh).to(dev)
+    out = torch.empty((m,), dtype=torch.float64, device=dev)
+    ctx = _cabi.Context.get(dev.index)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().ombo_scalarise(ctx.handle, C.byref(a), C.c_void_p(Fd.data_ptr()), m,
+                                               C.c_void_p(out.data_ptr()), current_stream_ptr(dev)))
+    return out.cpu().numpy()
 
 
 def posterior(models, X, precision="fp64", var_floor=1e-15):
@@ -327,15 +371,78 @@ def evaluate(models, spec, X, precision="fp64"):
     return r.acq.cpu().numpy()
 
 
-def propose(models, spec, pool, precision="fp64", refine_rounds=0, refine_candidates=1 << 14, refine_shrink=0.125):
+def polish(models, spec, starts, lo, hi, max_iter=30, fd_step=1e-5, precision="fp64"):
+    """local refinement of the best pool candidates, mirroring the `polish=True` step of
+    scipy's differential_evolution that every inner-optimiser call site of the reference runs after its global phase
+    (optimisers.py:87,118,366; cparego.py:94,544; emo.py:240 -- scipy polishes with
+    `minimize(fun, x, method="L-BFGS-B", bounds=...)` and finite-difference gradients).
+
+    `starts` (k, d): every start is polished by its own bounded L-BFGS-B run on the host; ALL acquisition evaluations
+    go through the GPU scoring kernels -- the objective value and the 2 d central-difference points of a gradient are
+    ONE batched scoring call of 2 d + 1 candidates (FP64 mode: finite differences need the smooth arithmetic).
+    Returns (x_best (d,), acq_best, per-start acquisition values (k,))."""
+    from scipy.optimize import minimize
+    models = _models_list(models)
+    lo = np.asarray(lo, dtype=np.float64)
+    hi = np.asarray(hi, dtype=np.float64)
+    starts = np.atleast_2d(np.asarray(starts, dtype=np.float64))
+    d = starts.shape[1]
+    h = fd_step * (hi - lo)
+
+    def fun_and_grad(x):
+        # forward / backward points clipped to the box; one GPU call for value + gradient
+        xp = np.minimum(x + h, hi)
+        xm = np.maximum(x - h, lo)
+        batch = np.vstack([x[None, :], np.where(np.eye(d, dtype=bool), xp[None, :], x[None, :]),
+                           np.where(np.eye(d, dtype=bool), xm[None, :], x[None, :])])
+        v = evaluate(models, spec, batch, precision=precision)
+        v = np.where(np.isfinite(v), v, -1e300)
+        g = (v[1:d + 1] - v[d + 1:]) / np.maximum(xp - xm, 1e-300)
+        return -v[0], -g
+
+    best_x, best_v, vals = None, -np.inf, []
+    for x0 in starts:
+        res = minimize(fun_and_grad, np.clip(x0, lo, hi), jac=True, method="L-BFGS-B", bounds=list(zip(lo, hi)),
+                       options=dict(maxiter=max_iter))
+        v = float(evaluate(models, spec, res.x[None, :], precision=precision)[0])
+        v0 = float(evaluate(models, spec, np.clip(x0, lo, hi)[None, :], precision=precision)[0])
+        xk, vk = (res.x, v) if (np.isfinite(v) and v >= v0) else (np.clip(x0, lo, hi), v0)    # never worse than the start
+        vals.append(vk)
+        if vk > best_v:
+            best_x, best_v = xk, vk
+    return best_x, best_v, np.asarray(vals)
+
+
+def top_candidates(models, spec, pool, k, precision="fp64", head=1 << 18):
+    """The k best candidates among the first `head` rows of `pool` (acquisition values materialised for that head only)
+    as (X (k, d) ndarray, values (k,)).  Used to seed `polish` next to the pool winner."""
+    models = _models_list(models)
+    dev = models[0].device
+    m = min(pool.m, head)
+    sub = pool.shard(0, 1)
+    sub = CandidatePool(m=m, d=pool.d, X=None if pool.X is None else pool.X[:m], lo=pool.lo, hi=pool.hi, seed=pool.seed,
+                        index_base=pool.index_base)
+    r = score(models, spec, sub, precision=precision, want_acq=True, want_best=False)
+    acq = torch.nan_to_num(r.acq, nan=-float("inf"))
+    vals, idx = torch.topk(acq, min(k, m))
+    rows = torch.stack([sub.rows(int(i) + pool.index_base, 1, device=dev)[0] for i in idx.cpu()])
+    return rows.cpu().numpy(), vals.cpu().numpy()
+
+
+def propose(models, spec, pool, precision="fp64", refine_rounds=0, refine_candidates=1 << 14, refine_shrink=0.125,
+            polish_top_k=0, polish_iters=30):
     """Scores the pool and returns (x_best (d,) ndarray, -acq_best, global_index), mirroring
     `(res.x, res.fun)` of the reference's `differential_evolution(obj, bounds)` call sites.
 
-    refine_rounds > 0 zooms in on the winner the way DE's `polish=True` does
-    after its global phase (optimisers.py:118 defaults): each round scores `refine_candidates` fresh
-    points in a box shrunk by `refine_shrink` around the incumbent (clipped to the pool's box) with
-    the same kernels and keeps the better point; the returned index is -1 once a refined point wins."""
+    Two refinements of the winner, both with the same scoring kernels:
+    * refine_rounds > 0: zoom -- each round scores `refine_candidates` fresh points in a box shrunk by `refine_shrink`
+      around the incumbent (clipped to the pool's box) and keeps the better point;
+    * polish_top_k > 0: DE's `polish=True` (optimisers.py:118 defaults) -- bounded L-BFGS-B from the pool winner and the
+      next best `polish_top_k - 1` candidates of the pool head, gradients by batched finite differences on the GPU
+      (`polish`).
+    The returned index is -1 once a refined point wins."""
     models = _models_list(models)
+    precision = resolve_precision(models, precision)
     r = score(models, spec, pool, precision=precision)
     dev = models[0].device
     x = pool.rows(r.best_index, 1, device=dev)[0].cpu().numpy()
@@ -351,6 +458,15 @@ def propose(models, spec, pool, precision="fp64", refine_rounds=0, refine_candid
             if rr.best_value > best:
                 best, index = rr.best_value, -1
                 x = sub.rows(rr.best_index, 1, device=dev)[0].cpu().numpy()
+    if polish_top_k > 0 and pool.lo is not None:
+        starts = x[None, :]
+        if polish_top_k > 1:
+            extra, _ = top_candidates(models, spec, pool, polish_top_k - 1, precision=precision)
+            starts = np.vstack([starts, extra])
+        xp, vp, _ = polish(models, spec, starts, pool.lo, pool.hi, max_iter=polish_iters)
+        # compare in the arithmetic the polish ran in (FP64); the pool winner's own value is vals[0] >= its start value
+        if vp > float(evaluate(models, spec, x[None, :], precision="fp64")[0]):
+            x, best, index = xp, vp, -1
     return x, -best, index
 
 
@@ -360,6 +476,7 @@ def propose_host(models, spec, X_host, precision="fp64", index_base=0):
     the 16-byte result is read back.  Returns (best_value, best_global_index)."""
     models = _models_list(models)
     dev = models[0].device
+    precision = resolve_precision(models, precision)
     if torch.is_tensor(X_host):
         if X_host.is_cuda:
             raise ValueError("propose_host takes host memory")

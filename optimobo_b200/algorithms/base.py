@@ -106,18 +106,8 @@ class PoolOptimiserBase:
         return model
 
     def _precision_for(self, models):
-        if self.precision != "auto":
-            return self.precision
-        from .. import _cabi
-        # tiny GPs: FP64 is cheap.  Otherwise the fast mode is used exactly where its accuracy is guaranteed:
-        # d <= 24 and a well-conditioned factor on every model (GPModel.conditioning, scripts/cond_study.py) --
-        # many points per length-scale in few dimensions (README MyProblem: kappa ~ 1e8) run FP64.
-        n = max(m.n for m in models)
-        d = models[0].d
-        if not (_cabi.fast_path_available() and n >= 64 and d <= 24):
-            return "fp64"
-        from ..gp import GPModel
-        return "fast" if max(m.conditioning for m in models) <= GPModel.FAST_MODE_CONDITIONING_LIMIT else "fp64"
+        from ..acquisition import resolve_precision
+        return resolve_precision(models, self.precision)
 
     # ---- the seam: pool scoring + arg-max instead of DE / EA ---------------------------------
     def _propose(self, models, spec):

@@ -20,6 +20,14 @@
 
 __device__ __forceinline__ double Phi(double t) { return 0.5 * erfc(-t * 0.70710678118654752440); }
 __device__ __forceinline__ double phi(double t) { return exp(-(t * t) / 2.0) / 2.50662827463100050242; }
+// FP32 twins for the fast precision mode (tolerance 1e-3): erfcf keeps its relative accuracy in the tails,
+// exp goes through MUFU.EX2 -- the FP64 pipe of the B200 is ~60x narrower than the FP32 one
+__device__ __forceinline__ float Phi(float t) { return 0.5f * erfcf(-t * 0.70710678f); }
+__device__ __forceinline__ float phi(float t) { return __expf(-0.5f * t * t) * 0.39894228f; }
+__device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
+__device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
+__device__ __forceinline__ float fmax_t(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double fmax_t(double a, double b) { return fmax(a, b); }
 
 // ---- scalarisations (scalarisations.py) --------------------------------------------------
 __device__ double scalarise(const ombo_acq &a, const double *F) {
@@ -108,9 +116,10 @@ __device__ double scalarise(const ombo_acq &a, const double *F) {
 }
 
 // ---- EI ----------------------------------------------------------------------------------
-__device__ __forceinline__ double ei_value(double mu, double var, double best, double eps) {
-  double s = sqrt(var + eps);
-  double g = (best - mu) / (s + 1e-10);
+template <typename T>
+__device__ __forceinline__ T ei_value(T mu, T var, T best, T eps) {
+  T s = sqrt_t(var + eps);
+  T g = (best - mu) / (s + (T)1e-10);
   return s * (g * Phi(g) + phi(g));
 }
 
@@ -130,52 +139,57 @@ __device__ __forceinline__ BestPair warp_best(BestPair b) {
 
 extern __shared__ __align__(16) double acq_smem[];
 
+// T = double: the reference's arithmetic (FP64 precision mode, all goldens).  T = float: the fast precision mode
+// (tolerance 1e-3) -- same formulas on the FP32 pipe with erfcf / MUFU exp; the expected decomposition always runs
+// in double (ExponentialWeightedCriterion overflows FP32, WeightedProduct's 1e5 offset eats its digits).
+template <typename T>
 __global__ void __launch_bounds__(ACQ_THREADS)
 k_acquire(ombo_acq a, int n_gp, const double *__restrict__ mu, const double *__restrict__ var,
           long long m, long long ld, long long index_base, double *__restrict__ out_acq,
           ombo_best *__restrict__ partials) {
   // stage the per-iteration constants
+  T *cst = reinterpret_cast<T *>(acq_smem);
   int n_stage = 0;
   const double *src = nullptr;
   if (a.kind == OMBO_ACQ_EHVI2D) { n_stage = 2 * (a.n_pf + 2); src = a.stripes; }
   else if (a.kind == OMBO_ACQ_HV_POI) { n_stage = a.n_cells * 2 * a.n_obj; src = a.cells; }
   else if (a.kind == OMBO_ACQ_EHVI3D || a.kind == OMBO_ACQ_EXPECTED_DECOMP) { n_stage = a.n_samples * a.n_obj; src = a.cache; }
-  for (int e = threadIdx.x; e < n_stage; e += ACQ_THREADS) acq_smem[e] = src[e];
+  for (int e = threadIdx.x; e < n_stage; e += ACQ_THREADS) cst[e] = (T)src[e];
   __syncthreads();
 
   const long long c = (long long)blockIdx.x * ACQ_THREADS + threadIdx.x;
   double val = -INFINITY;
   if (c < m) {
-    double mus[OMBO_MAX_GP], vars[OMBO_MAX_GP];
-    for (int g = 0; g < n_gp; ++g) { mus[g] = mu[g * ld + c]; vars[g] = var[g * ld + c]; }
-    double r = nan("");
+    T mus[OMBO_MAX_GP], vars[OMBO_MAX_GP];
+    for (int g = 0; g < n_gp; ++g) { mus[g] = (T)mu[g * ld + c]; vars[g] = (T)var[g * ld + c]; }
+    T r = (T)nan("");
     switch (a.kind) {
       case OMBO_ACQ_EHVI2D: {
         const int P = a.n_pf;
-        const double *y1 = acq_smem, *y2 = acq_smem + (P + 2);
+        const T *y1 = cst, *y2 = cst + (P + 2);
         const bool exact = (a.semantics == OMBO_SEM_EXACT);
         // reference: 'sigma' = flattened sample covariance (util_functions.py:163,167,:115)
-        const double s0 = exact ? sqrt(vars[0]) : vars[0] * a.cache_c00;
-        const double s1 = exact ? sqrt(vars[1]) : vars[0] * a.cache_c01;
-        const double m0 = mus[0], m1 = mus[1];
-        double sum1 = 0.0, sum2 = 0.0;
-        double tp = (y1[0] - m0) / s0;
-        double cdf_p = Phi(tp), pdf_p = phi(tp);
+        const T s0 = exact ? sqrt_t(vars[0]) : vars[0] * (T)a.cache_c00;
+        const T s1 = exact ? sqrt_t(vars[1]) : vars[0] * (T)a.cache_c01;
+        const T m0 = mus[0], m1 = mus[1];
+        T sum1 = 0, sum2 = 0;
+        T tp = (y1[0] - m0) / s0;
+        T cdf_p = Phi(tp), pdf_p = phi(tp);
         for (int i = 1; i <= P; ++i) {
-          double t = (y1[i] - m0) / s0;
-          double cdf_t = Phi(t), pdf_t = phi(t);
-          double t2 = (y2[i] - m1) / s1;
-          double psi2 = s1 * phi(t2) + (y2[i] - m1) * Phi(t2);
+          T t = (y1[i] - m0) / s0;
+          T cdf_t = Phi(t), pdf_t = phi(t);
+          T t2 = (y2[i] - m1) / s1;
+          T psi2 = s1 * phi(t2) + (y2[i] - m1) * Phi(t2);
           sum1 = sum1 + (y1[i - 1] - y1[i]) * cdf_t * psi2;
-          double psi_a = s0 * pdf_p + (y1[i - 1] - m0) * cdf_p;
-          double psi_b = s0 * pdf_t + (y1[i - 1] - m0) * cdf_t;
+          T psi_a = s0 * pdf_p + (y1[i - 1] - m0) * cdf_p;
+          T psi_b = s0 * pdf_t + (y1[i - 1] - m0) * cdf_t;
           sum2 = sum2 + (psi_a - psi_b) * psi2;
           cdf_p = cdf_t; pdf_p = pdf_t;
         }
         if (exact) {   // the (P+1)-th stripe the reference drops; y1[P+1] = -inf taken as a limit
-          double t2 = (y2[P + 1] - m1) / s1;
-          double psi2 = s1 * phi(t2) + (y2[P + 1] - m1) * Phi(t2);
-          double psi_a = s0 * pdf_p + (y1[P] - m0) * cdf_p;
+          T t2 = (y2[P + 1] - m1) / s1;
+          T psi2 = s1 * phi(t2) + (y2[P + 1] - m1) * Phi(t2);
+          T psi_a = s0 * pdf_p + (y1[P] - m0) * cdf_p;
           sum2 = sum2 + psi_a * psi2;
         }
         r = sum1 + sum2;
@@ -184,52 +198,54 @@ k_acquire(ombo_acq a, int n_gp, const double *__restrict__ mu, const double *__r
       case OMBO_ACQ_EXPECTED_DECOMP: {
         const int k = a.n_obj, S = a.n_samples;
         const bool exact = (a.semantics == OMBO_SEM_EXACT);
-        double sd[OMBO_MAX_OBJ];
-        for (int i = 0; i < k; ++i) sd[i] = sqrt(exact ? vars[i] : vars[0]);   // util_functions.py:233
-        double total = 0.0;
+        T sd[OMBO_MAX_OBJ];
+        for (int i = 0; i < k; ++i) sd[i] = sqrt_t(exact ? vars[i] : vars[0]);   // util_functions.py:233
+        T total = 0;
         for (int j = 0; j < S; ++j) {
-          double Y[OMBO_MAX_OBJ];
-          for (int i = 0; i < k; ++i) Y[i] = acq_smem[j * k + i] * sd[i] + mus[i];
+          T Y[OMBO_MAX_OBJ];
+          for (int i = 0; i < k; ++i) Y[i] = cst[j * k + i] * sd[i] + mus[i];
           if (a.kind == OMBO_ACQ_EHVI3D) {
             bool inside = true;
-            double hv = 1.0;
-            for (int i = 0; i < k; ++i) { double df = a.ref[i] - Y[i]; inside = inside && (df >= 0.0); hv = (i == 0) ? df : hv * df; }
-            hv -= a.best;    // Sminus = HV(PF), hoisted (util_functions.py:198-199)
-            if (inside && hv > 0.0) total += hv;
+            T hv = 1;
+            for (int i = 0; i < k; ++i) { T df = (T)a.ref[i] - Y[i]; inside = inside && (df >= (T)0); hv = (i == 0) ? df : hv * df; }
+            hv -= (T)a.best;    // Sminus = HV(PF), hoisted (util_functions.py:198-199)
+            if (inside && hv > (T)0) total += hv;
           } else {
-            double g = scalarise(a, Y);
-            total += fmax(0.0, a.best - g);          // NaN-propagating like np.maximum? see below
-            if (isnan(g)) total = nan("");
+            double Yd[OMBO_MAX_OBJ];
+            for (int i = 0; i < k; ++i) Yd[i] = (double)Y[i];
+            double g = scalarise(a, Yd);
+            total += (T)fmax(0.0, a.best - g);
+            if (isnan(g)) total = (T)nan("");
           }
         }
-        r = total / (double)S;
+        r = total / (T)S;
       } break;
       case OMBO_ACQ_EI:
-        r = ei_value(mus[0], vars[0], a.best, a.var_eps[0]);
+        r = ei_value<T>(mus[0], vars[0], (T)a.best, (T)a.var_eps[0]);
         break;
       case OMBO_ACQ_CONSTRAINED_EI: {
-        r = ei_value(mus[0], vars[0], a.best, a.var_eps[0]);
-        double pof = 1.0;
-        for (int g = 1; g < n_gp; ++g) pof *= Phi((0.0 - mus[g]) / sqrt(vars[g] + a.var_eps[g]));
+        r = ei_value<T>(mus[0], vars[0], (T)a.best, (T)a.var_eps[0]);
+        T pof = 1;
+        for (int g = 1; g < n_gp; ++g) pof *= Phi(((T)0 - mus[g]) / sqrt_t(vars[g] + (T)a.var_eps[g]));
         r = r * pof;
       } break;
       case OMBO_ACQ_PARETO_EI:
-        r = mus[0] * ei_value(mus[1], vars[1], a.best, a.var_eps[1]);
+        r = mus[0] * ei_value<T>(mus[1], vars[1], (T)a.best, (T)a.var_eps[1]);
         break;
       case OMBO_ACQ_HV_POI: {
         const int k = 2;     // emo.py:21 "Only works for 2D so far"
-        double sd[2];
-        for (int i = 0; i < k; ++i) sd[i] = sqrt(vars[i] + a.var_eps[i]);
-        double poi = 0.0, imp = 0.0;
+        T sd[2];
+        for (int i = 0; i < k; ++i) sd[i] = sqrt_t(vars[i] + (T)a.var_eps[i]);
+        T poi = 0, imp = 0;
         for (int cix = 0; cix < a.n_cells; ++cix) {
-          const double *U = acq_smem + (size_t)cix * 2 * a.n_obj, *Lo = U + a.n_obj;
-          double p = 1.0, vol = 1.0;
+          const T *U = cst + (size_t)cix * 2 * a.n_obj, *Lo = U + a.n_obj;
+          T p = 1, vol = 1;
           bool valid = true;
           for (int i = 0; i < k; ++i) {
-            double pi = Phi((U[i] - mus[i]) / sd[i]) - Phi((Lo[i] - mus[i]) / sd[i]);
+            T pi = Phi((U[i] - mus[i]) / sd[i]) - Phi((Lo[i] - mus[i]) / sd[i]);
             p = (i == 0) ? pi : p * pi;
             valid = valid && (U[i] > mus[i]);
-            double e = U[i] - fmax(Lo[i], mus[i]);
+            T e = U[i] - fmax_t(Lo[i], mus[i]);
             vol = (i == 0) ? e : vol * e;
           }
           poi += p;
@@ -238,10 +254,10 @@ k_acquire(ombo_acq a, int n_gp, const double *__restrict__ mu, const double *__r
         r = poi * imp;
       } break;
       default:
-        r = 0.0;
+        r = 0;
     }
-    if (out_acq) out_acq[c] = r;
-    val = isnan(r) ? -INFINITY : r;
+    if (out_acq) out_acq[c] = (double)r;
+    val = isnan(r) ? -INFINITY : (double)r;
   }
   // ---- K5: block arg-max ----
   BestPair b;
@@ -285,6 +301,24 @@ __global__ void __launch_bounds__(1024) k_argmax_final(const ombo_best *__restri
   }
 }
 
+// the 12 scalarisation functions on explicit objective vectors (device twin of Scalarisation.__call__,
+// scalarisations.py:20-27): out[r] = g(F[r, :], w)
+__global__ void k_scalarise(ombo_acq a, const double *__restrict__ F, long long m, double *__restrict__ out) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  double f[OMBO_MAX_OBJ];
+  for (int i = 0; i < a.n_obj; ++i) f[i] = F[r * a.n_obj + i];
+  out[r] = scalarise(a, f);
+}
+
+int ombo_scalarise_impl(ombo_ctx *ctx, const ombo_acq *acq, const double *F, long long m, double *out, cudaStream_t s) {
+  if (m <= 0) return OMBO_OK;
+  k_scalarise<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(*acq, F, m, out);
+  ctx->launches += 1;
+  OMBO_CUDA(cudaGetLastError());
+  return OMBO_OK;
+}
+
 __global__ void k_best_init(ombo_best *best) { best->value = -INFINITY; best->index = -1; }
 
 __global__ void k_pack_key(const ombo_best *__restrict__ best, long long *__restrict__ key) {
@@ -313,7 +347,7 @@ int ombo_best_init(ombo_ctx *ctx, ombo_best *best_dev, cudaStream_t s) {
 
 int ombo_acquire(ombo_ctx *ctx, const ombo_acq *acq, int n_gp, const double *mu, const double *var,
                  long long m, long long ld, long long index_base, double *out_acq, ombo_best *best_dev,
-                 cudaStream_t s) {
+                 cudaStream_t s, bool fp32) {
   if (m <= 0) return OMBO_OK;
   int n_stage = 0;
   if (acq->kind == OMBO_ACQ_EHVI2D) n_stage = 2 * (acq->n_pf + 2);
@@ -321,16 +355,21 @@ int ombo_acquire(ombo_ctx *ctx, const ombo_acq *acq, int n_gp, const double *mu,
   else if (acq->kind == OMBO_ACQ_EHVI3D || acq->kind == OMBO_ACQ_EXPECTED_DECOMP) n_stage = acq->n_samples * acq->n_obj;
   size_t smem = (size_t)n_stage * 8;
   OMBO_CHECK(smem <= 200 * 1024, "acquisition constants (%zu B) exceed shared memory", smem);
-  static size_t attr_smem = 48 * 1024;
-  if (smem > attr_smem) {
-    OMBO_CUDA(cudaFuncSetAttribute(k_acquire, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+  // FP32 arithmetic only in the fast precision mode, and never for the expected decomposition (see k_acquire)
+  fp32 = fp32 && acq->kind != OMBO_ACQ_EXPECTED_DECOMP && !ctx->knobs.acq_fp64;
+  if (smem > 48 * 1024) {   // per (function, device): set whenever the opt-in is needed
+    OMBO_CUDA(cudaFuncSetAttribute(k_acquire<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OMBO_CUDA(cudaFuncSetAttribute(k_acquire<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   int blocks = (int)((m + ACQ_THREADS - 1) / ACQ_THREADS);
   int rc = ombo_ws_reserve(&ctx->ws_partial, &ctx->ws_partial_bytes, (size_t)blocks * sizeof(ombo_best));
   if (rc) return rc;
-  k_acquire<<<blocks, ACQ_THREADS, smem, s>>>(*acq, n_gp, mu, var, m, ld, index_base, out_acq,
-                                              (ombo_best *)ctx->ws_partial);
+  if (fp32)
+    k_acquire<float><<<blocks, ACQ_THREADS, smem, s>>>(*acq, n_gp, mu, var, m, ld, index_base, out_acq,
+                                                       (ombo_best *)ctx->ws_partial);
+  else
+    k_acquire<double><<<blocks, ACQ_THREADS, smem, s>>>(*acq, n_gp, mu, var, m, ld, index_base, out_acq,
+                                                        (ombo_best *)ctx->ws_partial);
   ctx->launches += 1;
   if (best_dev) {
     k_argmax_final<<<1, 1024, 0, s>>>((const ombo_best *)ctx->ws_partial, blocks, best_dev);

@@ -1,5 +1,6 @@
 // C-ABI entry points (include/optimobo_b200.h).  Plain pointers and sizes only.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "candidates.cuh"
 
@@ -53,6 +54,22 @@ int ombo_ctx_create(int device, ombo_ctx **out) {
   memset(c, 0, sizeof(*c));
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
+  {   // environment knobs: read here, once, never on the launch path
+    auto geti = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
+    ombo_knobs &k = c->knobs;
+    k.fast_mode = geti("OMBO_FAST_MODE", 0);
+    k.fast_cluster = geti("OMBO_FAST_CLUSTER", 1);
+    k.fast_dbg = geti("OMBO_FAST_DBG", 0);
+    k.fast_profile = getenv("OMBO_FAST_PROFILE") != nullptr;
+    k.fast_notrim = getenv("OMBO_FAST_NOTRIM") != nullptr;
+    k.fast_nocache = getenv("OMBO_FAST_NOCACHE") != nullptr;
+    k.fast_zerocache = getenv("OMBO_FAST_ZEROCACHE") != nullptr;
+    k.fast_mean_in_main = getenv("OMBO_FAST_MEAN_IN_MAIN") != nullptr;
+    k.fast_gen_warps = geti("OMBO_FAST_GEN_WARPS", 16);
+    k.no_f8c = getenv("OMBO_NO_F8C") != nullptr;
+    { const char *e = getenv("OMBO_F8C_KAPPA"); k.f8c_kappa = e ? atof(e) : OMBO_F8C_KAPPA_DEFAULT; }
+    k.acq_fp64 = getenv("OMBO_ACQ_FP64") != nullptr;
+  }
   OMBO_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
     OMBO_CUDA(cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
@@ -77,6 +94,7 @@ int ombo_ctx_destroy(ombo_ctx *c) {
     cudaEventDestroy(c->ev_consumed[i]);
   }
   if (c->prof_ev[0]) for (int i = 0; i < 2 * OMBO_PROF_MAX; ++i) cudaEventDestroy(c->prof_ev[i]);
+  if (c->prof_dev) cudaFree(c->prof_dev);
   if (c->ws_best) cudaFree(c->ws_best);
   if (c->pinned_best) cudaFreeHost(c->pinned_best);
   cudaStreamDestroy(c->copy_stream);
@@ -226,7 +244,7 @@ static int score_pass(ombo_ctx *ctx, const ombo_gp *gps, int n_gp, const ombo_po
   }
   if (acq->kind != OMBO_ACQ_NONE)
     return ombo_acquire(ctx, acq, n_gp, mu, var, count, ld, pd.index_base, out_acq ? out_acq + first : nullptr,
-                        best_dev, s);
+                        best_dev, s, precision == OMBO_PREC_FAST);
   return OMBO_OK;
 }
 
@@ -316,6 +334,15 @@ int ombo_acquire_posterior(ombo_ctx *ctx, const ombo_acq *acq, int n_gp, const d
   cudaStream_t s = (cudaStream_t)stream;
   if (best_dev) { rc = ombo_best_init(ctx, best_dev, s); if (rc) return rc; }
   return ombo_acquire(ctx, acq, n_gp, mu, var, m, ld, index_base, out_acq, best_dev, s);
+}
+
+int ombo_scalarise(ombo_ctx *ctx, const ombo_acq *acq, const double *F, int64_t m, double *out, void *stream) {
+  OMBO_CHECK(ctx && acq && F && out, "scalarise: NULL argument");
+  OMBO_CHECK(acq->n_obj >= 1 && acq->n_obj <= OMBO_MAX_OBJ, "scalarise: n_obj=%d out of range (1..%d)", acq->n_obj, OMBO_MAX_OBJ);
+  OMBO_CHECK(acq->scalarisation >= 0 && acq->scalarisation <= OMBO_SC_APD, "scalarise: unknown scalarisation %d", acq->scalarisation);
+  OMBO_CHECK(m >= 0, "scalarise: negative m");
+  OMBO_CUDA(cudaSetDevice(ctx->device));
+  return ombo_scalarise_impl(ctx, acq, F, m, out, (cudaStream_t)stream);
 }
 
 __global__ void k_pool_rows(PoolDev pool, long long first, long long count, double *__restrict__ out) {

@@ -13,6 +13,7 @@
 #define OMBO_NB 64            // Cholesky / triangular-inverse block size
 #define OMBO_PAD 128          // n_pad granularity (GEMM N-chunk)
 #define OMBO_PROF_MAX 4096
+#define OMBO_F8C_KAPPA_DEFAULT 100.0   // conditioning limit of the f8c operand format (measured)
 #define OMBO_CHUNK (1 << 20)  // candidates scored per pass through the posterior workspace
 
 void ombo_set_error(const char *fmt, ...);
@@ -35,10 +36,25 @@ void ombo_set_error(const char *fmt, ...);
     }                                                                                \
   } while (0)
 
+// environment knobs, read ONCE when the context is created (never on the launch path)
+struct ombo_knobs {
+  int fast_mode;          // OMBO_FAST_MODE: 0 = default; 1 / 2 / 4 = experimental variants of the 16-bit x3 kernels
+  int fast_cluster;       // OMBO_FAST_CLUSTER (mode 1 only)
+  int fast_dbg;           // OMBO_FAST_DBG: timing experiments (results are garbage)
+  int fast_profile;       // OMBO_FAST_PROFILE: per-CTA wait-cycle counters printed to stderr
+  int fast_notrim, fast_nocache, fast_zerocache, fast_mean_in_main;
+  int fast_gen_warps;     // OMBO_FAST_GEN_WARPS: 8 or 16 K1 generator warps in the f8c kernel
+  int no_f8c;             // OMBO_NO_F8C: never choose the fp16 + 2 x e4m3 operand format
+  double f8c_kappa;       // OMBO_F8C_KAPPA: conditioning limit of that format
+  int acq_fp64;           // OMBO_ACQ_FP64: keep the FP64 acquisition kernel in fast mode
+};
+
 struct ombo_ctx {
   int device;
   int num_sms;
   int64_t launches;
+  ombo_knobs knobs;
+  long long *prof_dev;    // per-CTA wait counters of the fast kernels (OMBO_FAST_PROFILE)
   // workspaces (grown on demand, freed in ctx_destroy)
   void *ws_post;      size_t ws_post_bytes;      // posterior mu/var chunk buffers
   void *ws_scratch;   size_t ws_scratch_bytes;   // FP64 K* tiles (L2 resident) / fast-path scratch
@@ -153,10 +169,13 @@ int ombo_posterior_fp64(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
                         double *mu, double *var, bool want_var, cudaStream_t s);
 int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, long long m,
                         double *mu, double *var, bool want_var, cudaStream_t s);
+int ombo_posterior_fast8(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, long long m,
+                         double *mu, double *var, cudaStream_t s);
 int ombo_fast_path_built();
 int ombo_acquire(ombo_ctx *ctx, const ombo_acq *acq, int n_gp, const double *mu, const double *var,
                  long long m, long long ld, long long index_base, double *out_acq,
-                 ombo_best *best_dev, cudaStream_t s);
+                 ombo_best *best_dev, cudaStream_t s, bool fp32 = false);
+int ombo_scalarise_impl(ombo_ctx *ctx, const ombo_acq *acq, const double *F, long long m, double *out, cudaStream_t s);
 int ombo_best_init(ombo_ctx *ctx, ombo_best *best_dev, cudaStream_t s);
 int ombo_pack_key_impl(ombo_ctx *ctx, const ombo_best *best_dev, long long *key_dev, cudaStream_t s);
 int ombo_potrf_lower_impl(ombo_ctx *ctx, double *L, int np, int n, double *dinv, int *status, cudaStream_t s);

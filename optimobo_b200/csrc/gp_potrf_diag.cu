@@ -2,9 +2,10 @@
 // optimiser needs five minutes for the two fully unrolled 64-step loops at -O3 (everything else in the library
 // builds in under a minute).  -Xcicc -O1 compiles it in three seconds but leaves the 64-element inverse column
 // in local memory: measured 7.9 ms instead of 4.5 ms for the two refreshes of the C5 workload, so -O3 stays.
-#include "common.cuh"
+// (no project headers on purpose: this file must not rebuild when common.cuh changes)
+#include <cuda_runtime.h>
 
-#define NB OMBO_NB
+#define NB 64      // == OMBO_NB (common.cuh); checked by a static_assert in gp_refresh.cu
 
 // ------------------------------------------------------------------------------------------
 // diagonal block: Cholesky of a 64x64 block + inverse of its triangular factor, 64 threads.

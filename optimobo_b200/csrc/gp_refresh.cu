@@ -84,6 +84,7 @@ __global__ void k_build_K(const double *__restrict__ xs, int n, int d, int n_pad
 // k_potrf_diag (Cholesky + inverse of one 64x64 diagonal block) lives in gp_potrf_diag.cu: its fully unrolled
 // 64-step register kernels take the NVVM optimiser five minutes at -O3 -- kept apart so that edits here build fast
 void ombo_launch_potrf_diag(double *A, int ld, int kb, int n, double *dinv, int *status, cudaStream_t s);
+static_assert(OMBO_NB == 64, "gp_potrf_diag.cu hard-codes the 64x64 diagonal block");
 
 // C(64x64) (+)= sign * As(64x64) * Bs(64x64)^T with both operands k-contiguous in smem
 __device__ __forceinline__ void gemm64_abt(double (*As)[LDS], double (*Bs)[LDS], double acc[4][4],
@@ -250,28 +251,43 @@ __global__ void k_absmax_lower(const double *__restrict__ Linv, const double *__
   if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(v));
 }
 
-// zero the padding of L^-1 and emit the fast-path operands B = s * sigma_f2 * L^-1 as 16-bit hi + lo planes.
+// zero the padding of L^-1 and emit the fast-path operands B = s * sigma_f2 * L^-1 as planes.
 // The format is chosen here, on the device, from the conditioning proxy kappa = (max L_ii / min L_ii)^2:
-//   kappa <= 100: bf16 planes, s = 1 (8 significant bits each, 16 in the 3-product split: sigma good to 1e-4 sigma_f
-//                 at that conditioning, and the tensor core runs bf16 ~3.5 % faster than fp16 at the power cap);
-//   kappa  > 100: fp16 planes (11 + 11 bits), s = the power of two that brings max |B| into [8192, 16384) so that
-//                 ill-conditioned factors stay inside fp16's range; the generators then also use direct-difference
-//                 distances.  bscale[1] = s, [2] = 1 / s^2, [3] = 1.0 for fp16 / 0.0 for bf16.
-__global__ void k_finalize(double *__restrict__ Linv, int n, int n_pad, double sf2, int allow_f16,
+//   f8c  (kappa <= f8c_kappa, caller allows it): hi plane fp16 with s = the power of two that brings max |B| into
+//        [8192, 16384); the lo field holds two e4m3 planes, e4m3(2^-12 B) and e4m3(B - fp16(B)) -- the operands of
+//        the two correction products of posterior_fast8.cu (2.0 tensor units per MAC);
+//   bf16 (kappa <= 100 otherwise): bf16 hi + lo planes, s = 1 (16-bit x3 split, 3.0 units);
+//   fp16 (kappa  > 100, caller allows it): fp16 hi + lo planes with the same power-of-two scale; the generators then
+//        also use direct-difference distances.
+// bscale[1] = s, [2] = 1 / s^2, [3] = format (0 bf16, 1 fp16, 2 f8c).
+#include <cuda_fp8.h>
+__device__ __forceinline__ int plane_format(const double *bscale, int allow, double f8c_kappa) {
+  const double ratio = bscale[2] > 0.0 ? bscale[1] / bscale[2] : 1.0;       // max L_ii / min L_ii
+  const double kappa = ratio * ratio;
+  if ((allow & OMBO_GP_F8C_PLANES) && kappa <= f8c_kappa) return 2;
+  if ((allow & OMBO_GP_FP16_PLANES) && kappa > 100.0) return 1;
+  return 0;
+}
+__global__ void k_finalize(double *__restrict__ Linv, int n, int n_pad, double sf2, int allow, double f8c_kappa,
                            unsigned short *__restrict__ bhi, unsigned short *__restrict__ blo, double *__restrict__ bscale,
                            const double *__restrict__ alpha, float *__restrict__ alpha32) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)n_pad * n_pad;
   if (e >= total) return;
-  const double ratio = bscale[2] > 0.0 ? bscale[1] / bscale[2] : 1.0;       // max L_ii / min L_ii
-  const bool f16 = allow_f16 && ratio * ratio > 100.0;
+  const int fmt = plane_format(bscale, allow, f8c_kappa);
   const double mx = bscale[0] * sf2;
-  const double sc = (f16 && mx > 0.0) ? exp2(floor(log2(16384.0 / mx))) : 1.0;
+  const double sc = (fmt != 0 && mx > 0.0) ? exp2(floor(log2(16384.0 / mx))) : 1.0;
   int j = (int)(e / n_pad), i = (int)(e % n_pad);
   double v = Linv[e];
   if (j >= n || i >= n || i > j) { v = 0.0; Linv[e] = 0.0; }
   const double t = v * sf2 * sc;
-  if (f16) {
+  if (fmt == 2) {
+    const __half h = __float2half_rn((float)t);
+    bhi[e] = __half_as_ushort(h);
+    unsigned char *c1 = (unsigned char *)blo, *c2 = c1 + total;
+    c1[e] = (unsigned char)__nv_cvt_float_to_fp8((float)(t * (1.0 / 4096.0)), __NV_SATFINITE, __NV_E4M3);
+    c2[e] = (unsigned char)__nv_cvt_float_to_fp8((float)(t - (double)__half2float(h)), __NV_SATFINITE, __NV_E4M3);
+  } else if (fmt == 1) {
     const __half h = __float2half_rn((float)t);
     const __half l = __float2half_rn((float)(t - (double)__half2float(h)));
     bhi[e] = __half_as_ushort(h);
@@ -285,15 +301,14 @@ __global__ void k_finalize(double *__restrict__ Linv, int n, int n_pad, double s
   if (e < (size_t)n_pad) alpha32[e] = (float)(alpha[e] * sf2);
 }
 
-// the per-GP constants the fast kernels read: [1] = s, [2] = 1 / s^2, [3] = format flag (after every thread of
+// the per-GP constants the fast kernels read: [1] = s, [2] = 1 / s^2, [3] = format (after every thread of
 // k_finalize has read the raw extrema: a separate launch)
-__global__ void k_publish_scale(double *__restrict__ bscale, double sf2, int allow_f16, int *__restrict__ status) {
-  const double ratio = bscale[2] > 0.0 ? bscale[1] / bscale[2] : 1.0;
-  const bool f16 = allow_f16 && ratio * ratio > 100.0;
+__global__ void k_publish_scale(double *__restrict__ bscale, double sf2, int allow, double f8c_kappa, int *__restrict__ status) {
+  const int fmt = plane_format(bscale, allow, f8c_kappa);
   const double mx = bscale[0] * sf2;
-  const double sc = (f16 && mx > 0.0) ? exp2(floor(log2(16384.0 / mx))) : 1.0;
-  bscale[1] = sc; bscale[2] = 1.0 / (sc * sc); bscale[3] = f16 ? 1.0 : 0.0;
-  status[1] = f16 ? 1 : 0;            // read back by the host with the PD flag: OMBO_GP_FP16_PLANES for ombo_gp.reserved
+  const double sc = (fmt != 0 && mx > 0.0) ? exp2(floor(log2(16384.0 / mx))) : 1.0;
+  bscale[1] = sc; bscale[2] = 1.0 / (sc * sc); bscale[3] = (double)fmt;
+  status[1] = fmt;          // read back by the host with the PD flag: 1 -> OMBO_GP_FP16_PLANES, 2 -> OMBO_GP_F8C_PLANES
 }
 
 // ------------------------------------------------------------------------------------------
@@ -303,12 +318,9 @@ __global__ void k_publish_scale(double *__restrict__ bscale, double sf2, int all
 int ombo_potrf_lower_impl(ombo_ctx *ctx, double *L, int np, int n, double *dinv, int *status, cudaStream_t s) {
   const int nb = np / NB;
   const size_t sm2 = (size_t)2 * NB * LDS * sizeof(double);
-  static bool attr_set = false;
-  if (!attr_set) {
-    OMBO_CUDA(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-    OMBO_CUDA(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
-    attr_set = true;
-  }
+  // per (function, device): one process may drive several devices, so no process-wide "already set" flag
+  OMBO_CUDA(cudaFuncSetAttribute(k_trsm_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+  OMBO_CUDA(cudaFuncSetAttribute(k_syrk_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
   for (int kb = 0; kb < nb; ++kb) {
     ombo_launch_potrf_diag(L, np, kb, n, dinv, status, s);
     ctx->launches += 1;
@@ -359,10 +371,12 @@ int ombo_refresh_impl(ombo_ctx *ctx, const ombo_gp_spec *sp, void *state, cudaSt
     OMBO_CUDA(cudaMemcpyAsync(bscale, init, 32, cudaMemcpyHostToDevice, s));
   }
   // fp16 planes only for callers that announce (spec->reserved bit 1) that they will pass the reported format on
-  const int allow_f16 = (sp->reserved & OMBO_GP_FP16_PLANES) ? 1 : 0;
+  int allow = sp->reserved & (OMBO_GP_FP16_PLANES | OMBO_GP_F8C_PLANES);
+  if (d > 12 || ctx->knobs.no_f8c) allow &= ~OMBO_GP_F8C_PLANES;       // the f8c kernel is instantiated for d <= 12
+  const double f8c_kappa = ctx->knobs.f8c_kappa;
   k_absmax_lower<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Linv, L, n, np, (unsigned long long *)bscale);
-  k_finalize<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Linv, n, np, sp->sigma_f2, allow_f16, bhi, blo, bscale, alpha, alpha32);
-  k_publish_scale<<<1, 1, 0, s>>>(bscale, sp->sigma_f2, allow_f16, status);
+  k_finalize<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(Linv, n, np, sp->sigma_f2, allow, f8c_kappa, bhi, blo, bscale, alpha, alpha32);
+  k_publish_scale<<<1, 1, 0, s>>>(bscale, sp->sigma_f2, allow, f8c_kappa, status);
   ctx->launches += 6;
   OMBO_CUDA(cudaGetLastError());
   int hstatus[4] = {0, 0, 0, 0};

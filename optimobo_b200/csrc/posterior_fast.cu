@@ -758,11 +758,9 @@ k_posterior_mean_fast(const FastParams prm) {
 }
 
 // ---- host side ------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef PFN_encodeTiled_t PFN_encodeTiled;
 
-static PFN_encodeTiled get_encode() {
+PFN_encodeTiled_t ombo_get_encode_tiled() {
   static PFN_encodeTiled fn = nullptr;
   if (!fn) {
     void *p = nullptr;
@@ -775,7 +773,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 static int make_b_map(CUtensorMap *map, const void *base, int n_pad, int box_rows, int rows = 0) {
-  PFN_encodeTiled enc = get_encode();
+  PFN_encodeTiled enc = ombo_get_encode_tiled();
   if (!enc) { ombo_set_error("cuTensorMapEncodeTiled is not available from the driver"); return OMBO_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)n_pad, (cuuint64_t)(rows ? rows : n_pad)};
   cuuint64_t strides[1] = {(cuuint64_t)n_pad * 2};
@@ -789,8 +787,8 @@ static int make_b_map(CUtensorMap *map, const void *base, int n_pad, int box_row
 }
 
 // the K* cache seen as rows of 128 B (one shared-memory stage = 256 rows), no swizzle: a straight copy
-static int make_linear_map(CUtensorMap *map, const void *base, size_t rows) {
-  PFN_encodeTiled enc = get_encode();
+int ombo_make_linear_map(CUtensorMap *map, const void *base, size_t rows) {
+  PFN_encodeTiled enc = ombo_get_encode_tiled();
   if (!enc) { ombo_set_error("cuTensorMapEncodeTiled is not available from the driver"); return OMBO_ERR_CUDA; }
   cuuint64_t dims[2] = {64, (cuuint64_t)rows};
   cuuint64_t strides[1] = {128};
@@ -810,11 +808,8 @@ static int launch_fast(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensorM
                        int grid, int cs, cudaStream_t s) {
   const size_t smem = (size_t)6 * STAGE_BYTES + (size_t)DP * FM * 4 + 2 * (size_t)(DP + 2) * FK * 4 +
                       8 * FM * 4 + 16 + 24 * 8 + 24 * 8 + 1024;   // barriers + TMEM slot, 1/lengthscale, alignment slack
-  static bool attr = false;
-  if (!attr) {
-    OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast<DP, R, MODE, GW, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  // set on every launch: the attribute belongs to the (function, device) pair, and one process may drive several devices
+  OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast<DP, R, MODE, GW, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(ctx, s);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -838,7 +833,8 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
     return OMBO_ERR_UNSUPPORTED;
   }
   long long tiles = (m + FM - 1) / FM;
-  if (!want_var && gp.d <= 12 && !getenv("OMBO_FAST_MEAN_IN_MAIN")) {
+  const ombo_knobs &kn = ctx->knobs;
+  if (!want_var && gp.d <= 12 && !kn.fast_mean_in_main) {
     // mean-only: the dedicated K1 kernel (two CTAs per SM; d <= 12 keeps 4 rows x d coordinates in registers)
     FastParams prm;
     prm.gp = gp; prm.pool = pool; prm.m = m; prm.mu_out = mu; prm.var_out = var; prm.mean_only = 1;
@@ -868,11 +864,12 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
   // (k_posterior_fast_dc, d <= 12).
   bool pair = false, wide = true, dc = false;
   int cs = 1;
-  { const char *e = getenv("OMBO_FAST_MODE"); const int mode = e ? atoi(e) : 3;
+  if (want_var && (gp.flags & OMBO_GP_F8C_PLANES)) return ombo_posterior_fast8(ctx, gp, pool, m, mu, var, s);
+  { const int mode = kn.fast_mode ? kn.fast_mode : 3;
     if (mode == 1) wide = false;
     else if (mode == 2) { wide = false; pair = true; }
     else if (mode == 4 && gp.d <= 12) { wide = false; pair = true; dc = true; } }
-  if (!pair && !wide) { const char *e = getenv("OMBO_FAST_CLUSTER"); if (e) cs = atoi(e); if (cs != 1 && cs != 2 && cs != 4) cs = 1; if (tiles < cs) cs = 1; }
+  if (!pair && !wide) { cs = kn.fast_cluster; if (cs != 1 && cs != 2 && cs != 4) cs = 1; if (tiles < cs) cs = 1; }
   if (pair) cs = 2;
   CUtensorMap map_hi, map_lo;
   const int box_rows = wide ? 256 : (pair ? 128 : 128 / cs);
@@ -882,10 +879,10 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
   if (rc) return rc;
   FastParams prm;
   prm.gp = gp; prm.pool = pool; prm.m = m; prm.mu_out = mu; prm.var_out = var; prm.mean_only = want_var ? 0 : 1;
-  { const char *e = getenv("OMBO_FAST_DBG"); prm.dbg = e ? atoi(e) : 0; }
-  static long long *prof_dev = nullptr;
-  const bool want_prof = getenv("OMBO_FAST_PROFILE") != nullptr;
-  if (want_prof && !prof_dev) OMBO_CUDA(cudaMalloc(&prof_dev, 16 * 256 * sizeof(long long)));
+  prm.dbg = kn.fast_dbg;
+  const bool want_prof = kn.fast_profile != 0;
+  if (want_prof && !ctx->prof_dev) OMBO_CUDA(cudaMalloc(&ctx->prof_dev, 16 * 256 * sizeof(long long)));
+  long long *prof_dev = ctx->prof_dev;
   prm.prof = want_prof ? prof_dev : nullptr;
   if (want_prof) OMBO_CUDA(cudaMemsetAsync(prof_dev, 0, 16 * 256 * sizeof(long long), s));
   int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
@@ -895,19 +892,19 @@ int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
   CUtensorMap map_kc = map_hi;                 // pair variants: linear map of the K* cache; wide: 64-row boxes of B
   prm.trim_b = 0;
   if (wide && (const unsigned char *)gp.blo == (const unsigned char *)gp.bhi + (size_t)gp.n_pad * gp.n_pad * 2 &&
-      !getenv("OMBO_FAST_NOTRIM")) {
+      !kn.fast_notrim) {
     // the two bf16 planes are adjacent in the state blob: one map over (2 n_pad, n_pad) serves both
     rc = make_b_map(&map_kc, gp.bhi, gp.n_pad, 64, 2 * gp.n_pad);
     if (rc) return rc;
     prm.trim_b = 1;
   }
-  if (want_var && (dc || (gp.n_pad > 512 && !getenv("OMBO_FAST_NOCACHE")))) {   // dc: always; else only with > 1 TMEM pass
+  if (want_var && (dc || (gp.n_pad > 512 && !kn.fast_nocache))) {   // dc: always; else only with > 1 TMEM pass
     rc = ombo_ws_reserve(&ctx->ws_scratch, &ctx->ws_scratch_bytes, (size_t)grid * (gp.n_pad / FK) * STAGE_BYTES);
     if (rc) return rc;
     prm.kcache = (unsigned char *)ctx->ws_scratch;
-    if (getenv("OMBO_FAST_ZEROCACHE")) OMBO_CUDA(cudaMemsetAsync(prm.kcache, 0, (size_t)grid * (gp.n_pad / FK) * STAGE_BYTES, s));
+    if (kn.fast_zerocache) OMBO_CUDA(cudaMemsetAsync(prm.kcache, 0, (size_t)grid * (gp.n_pad / FK) * STAGE_BYTES, s));
     if (pair) {
-      rc = make_linear_map(&map_kc, prm.kcache, (size_t)grid * (gp.n_pad / FK) * 256);
+      rc = ombo_make_linear_map(&map_kc, prm.kcache, (size_t)grid * (gp.n_pad / FK) * 256);
       if (rc) return rc;
     }
   }

@@ -477,11 +477,7 @@ static int launch_fast_dc(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtens
                           const FastParams &prm, int grid, cudaStream_t s) {
   const size_t smem = (size_t)6 * STAGE_BYTES + (size_t)DP * FM * 4 + 3 * (size_t)(DP + 2) * FK * 4 +
                       16 + 24 * 8 + 24 * 8 + 1024;     // barriers + counters, 1/lengthscale, alignment slack
-  static bool attr = false;
-  if (!attr) {
-    OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast_dc<DP, R, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast_dc<DP, R, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per (function, device)
   ProfScope prof(ctx, s);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);

@@ -186,11 +186,7 @@ int ombo_posterior_fp64(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lon
   const size_t smem_b = (size_t)(2 * TM * SROW + 2 * NC * SROW) * 8;
   const size_t smem_a = (size_t)(TM * gp.d + gp.d * TCH) * 8;
   const size_t smem = smem_a > smem_b ? smem_a : smem_b;
-  static bool attr_set = false;
-  if (!attr_set) {
-    OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fp64, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_set = true;
-  }
+  OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fp64, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));   // per (function, device)
   long long tiles = (m + TM - 1) / TM;
   int grid = (int)(tiles < 2LL * ctx->num_sms ? tiles : 2LL * ctx->num_sms);
   size_t want = (size_t)grid * TM * gp.n_pad * 8;

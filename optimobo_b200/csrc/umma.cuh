@@ -127,6 +127,26 @@ __device__ __forceinline__ void mbar_arrive_n_cluster(uint32_t bar, uint32_t cou
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
 }
+// The same on a barrier of a cluster peer WITHOUT cluster-scope release semantics (default .release.cta, as CUTLASS'
+// ClusterBarrier::arrive does): the .release.cluster forms above compile to MEMBAR.ALL.GPU + ERRBAR, ~1000 cycles per
+// arrive on the critical path of every generator warp (ncu source view, profiles/r02_*).  The data these arrivals
+// publish sits in the arriving CTA's OWN shared memory, is ordered by the preceding fence.proxy.async / tcgen05 fence
+// and is read through the async proxy after the barrier has completed -- shared memory has no cache to flush.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n_remote(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_remote(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory");
+}
 // 2-SM TMA load: data lands in this CTA's smem, the transaction bytes are counted on the LEADER's barrier
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
   asm volatile(
@@ -215,6 +235,13 @@ struct FastParams {
 
 
 extern __shared__ __align__(1024) unsigned char fast_smem[];
+
+// host helpers shared by the fast-mode translation units (posterior_fast.cu)
+typedef CUresult (*PFN_encodeTiled_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled_t ombo_get_encode_tiled();
+int ombo_make_linear_map(CUtensorMap *map, const void *base, size_t rows);
 
 // posterior_fast_dc.cu: launches k_posterior_fast_dc for the instantiated dimension (d <= 12)
 int ombo_launch_fast_dc(ombo_ctx *ctx, const CUtensorMap &map_hi, const CUtensorMap &map_lo, const CUtensorMap &map_kc,

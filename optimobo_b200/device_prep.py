@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _cabi
-from .gp import current_stream_ptr
+from .gp import _as_device, current_stream_ptr
 
 
 def _dev_f64(a, device):
@@ -33,11 +33,11 @@ def _vec(v, k):
 
 def pareto_mask(Y, device="cuda:0"):
     """(n,) bool tensor on the device: True for the rows of Y (n,k) in the first non-dominated front."""
-    dev = torch.device(device)
+    dev = _as_device(device)
     Yd = _dev_f64(Y, dev)
     n, k = Yd.shape
     mask = torch.empty((n,), dtype=torch.uint8, device=dev)
-    ctx = _cabi.Context.get(dev.index or 0)
+    ctx = _cabi.Context.get(dev.index)
     with torch.cuda.device(dev):
         _cabi.check(_cabi.lib().ombo_pareto_mask(ctx.handle, C.c_void_p(Yd.data_ptr()), n, k,
                                                  C.c_void_p(mask.data_ptr()), current_stream_ptr(dev)))
@@ -55,11 +55,11 @@ def calc_pf(Y, device="cuda:0"):
 
 def hypervolume(points, ref_point, device="cuda:0"):
     """Exact dominated hypervolume (minimisation) of (p,k) points, k = 2 or 3."""
-    dev = torch.device(device)
+    dev = _as_device(device)
     P = _dev_f64(points, dev)
     p, k = P.shape
     out = torch.zeros((1,), dtype=torch.float64, device=dev)
-    ctx = _cabi.Context.get(dev.index or 0)
+    ctx = _cabi.Context.get(dev.index)
     with torch.cuda.device(dev):
         _cabi.check(_cabi.lib().ombo_hypervolume(ctx.handle, C.c_void_p(P.data_ptr()), p, k, _vec(ref_point, k),
                                                  C.c_void_p(out.data_ptr()), current_stream_ptr(dev)))
@@ -68,13 +68,13 @@ def hypervolume(points, ref_point, device="cuda:0"):
 
 def decompose_into_cells(pf, ideal_point, max_point, device="cuda:0"):
     """(p+1, 2, 2) cells of a 2-D front ([c][0] upper, [c][1] lower corner) as a device tensor."""
-    dev = torch.device(device)
+    dev = _as_device(device)
     P = _dev_f64(pf, dev)
     if P.shape[1] != 2:
         raise ValueError("cell decomposition is 2-D only (emo.py:21)")
     p = P.shape[0]
     cells = torch.empty((p + 1, 2, 2), dtype=torch.float64, device=dev)
-    ctx = _cabi.Context.get(dev.index or 0)
+    ctx = _cabi.Context.get(dev.index)
     with torch.cuda.device(dev):
         _cabi.check(_cabi.lib().ombo_cells_2d(ctx.handle, C.c_void_p(P.data_ptr()), p, _vec(ideal_point, 2),
                                               _vec(max_point, 2), C.c_void_p(cells.data_ptr()),

@@ -79,7 +79,7 @@ class GPModel:
         ell = (C.c_double * self.d)(*self.lengthscale.tolist())
         jitter = self.jitter
         for attempt in range(self.max_jitter_tries + 1):
-            spec = _cabi.GpSpec(n=self.n, d=self.d, kernel=self.kernel, reserved=2,   # fp16 planes allowed
+            spec = _cabi.GpSpec(n=self.n, d=self.d, kernel=self.kernel, reserved=2 | 4,   # fp16 and f8c planes allowed
                                 sigma_f2=self.variance, sigma_n2=self.noise, jitter=jitter,
                                 X=self.X.data_ptr(), y=self.y.data_ptr(), ell=ell)
             with torch.cuda.device(self.device):
@@ -94,9 +94,11 @@ class GPModel:
         self.effective_jitter = jitter
         self.refreshed = True
         self._conditioning = None
-        # word 1 of the status field: the refresh stored fp16 (1) or bf16 (0) operand planes for the fast mode
+        # word 1 of the status field: format of the fast mode's operand planes the refresh stored
+        # (0 bf16 x3, 1 fp16 x3, 2 "f8c" = fp16 + two e4m3 correction planes) -> ombo_gp.reserved flags
         st = self._field(_cabi.FIELD_STATUS, torch.int32, (4,)).cpu()
-        self._flags = 2 if int(st[1]) else 0          # OMBO_GP_FP16_PLANES
+        self.plane_format = ("bf16x3", "fp16x3", "f8c")[int(st[1])]
+        self._flags = (0, 2, 4)[int(st[1])]           # OMBO_GP_FP16_PLANES / OMBO_GP_F8C_PLANES
         return self
 
     # fast precision mode keeps sigma within 1e-3 sigma_f while `conditioning` stays below this (measured,
@@ -170,7 +172,7 @@ class GPModel:
         if Xd.shape != (m, self.d):
             raise ValueError(f"X must be ({m}, {self.d}), got {tuple(Xd.shape)}")
         out = torch.empty((m, S), dtype=torch.float64, device=self.device)
-        ctx = _cabi.Context.get(self.device.index or 0)
+        ctx = _cabi.Context.get(self.device.index)
         g = self.c_struct()
         jit = 1e-8 * self.variance if jitter is None else float(jitter)
         for attempt in range(max_jitter_tries + 1):
@@ -191,5 +193,5 @@ class GPModel:
         """Adopts the hyper-parameters of a fitted GPy GPRegression (reference models)."""
         kern = gpy_model.kern
         return cls(np.asarray(gpy_model.X), np.asarray(gpy_model.Y).reshape(-1),
-                   np.asarray(kern.lengthscale), float(kern.variance),
-                   noise=float(gpy_model.Gaussian_noise.variance), device=device)
+                   np.asarray(kern.lengthscale), float(np.asarray(kern.variance).reshape(-1)[0]),
+                   noise=float(np.asarray(gpy_model.Gaussian_noise.variance).reshape(-1)[0]), device=device)

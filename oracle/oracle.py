@@ -7,15 +7,17 @@ imports anything from here and has no CPU fallback.
 Pinning status (also in DESIGN.md):
   * acquisition arithmetic (rows a2-a11 of SURVEY.md section 8a): PINNED -- every
     function below is checked against the reference's own code executed in the
-    build container (oracle/ref_loader.py) by tests/test_oracle_vs_reference.py
-    and against committed fixtures minted from that code
-    (tests/golden/*.npz, script oracle/make_golden.py).
+    build container (oracle/ref_loader.py, oracle/make_golden.py) and pinned by
+    tests/test_oracle_golden.py against the committed fixtures minted from that
+    code (tests/golden/acq_golden.npz) and against the hand anchors of SURVEY 8c.
   * GP posterior (row a1): PARITY UNPINNED by the reference -- the arithmetic
     lives in GPy (gpy>=1.10.0, requirements.txt:5, un-vendored, not
     installable offline).  `gp_fit_state`/`gp_posterior` restate GPy's
     published algorithm (kern/src/stationary.py, exact_gaussian_inference.py,
     posterior.py) and are cross-checked against sklearn's
-    GaussianProcessRegressor, which *is* installed (tests/test_oracle_gp.py).
+    GaussianProcessRegressor, which *is* installed (tests/test_oracle_gp.py on
+    the CPU; tests/test_gpu_pins.py compares the CUDA posterior with sklearn
+    DIRECTLY -- the surface util_functions.py:265 calls).
 
 All citations are file:line into /root/reference/optimobo unless noted.
 """

@@ -28,7 +28,12 @@ import types
 
 import numpy as np
 
-_REF_CANDIDATES = [os.environ.get("OPTIMOBO_REF", ""), "/root/reference"]
+# Lookup order: $OPTIMOBO_REF, the read-only tree of the build container, and `baseline/_ref/` -- the
+# unmodified reference package installed by `python -m pip install --no-index --no-build-isolation --no-deps
+# --target baseline/_ref <copy of /root/reference>` (recorded in DESIGN.md; git-ignored, NOT gpurun-ignored, so it
+# travels to the GPU box and the reference's own call pattern can be timed there).
+_REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_REF_CANDIDATES = [os.environ.get("OPTIMOBO_REF", ""), "/root/reference", os.path.join(_REPO_ROOT, "baseline", "_ref")]
 
 
 def reference_root():
@@ -156,7 +161,7 @@ def load_reference():
         return types.SimpleNamespace(**_loaded)
     root = reference_root()
     if root is None:
-        raise RuntimeError("reference tree not present (expected /root/reference or $OPTIMOBO_REF)")
+        raise RuntimeError("reference tree not present (expected $OPTIMOBO_REF, /root/reference or baseline/_ref)")
     _install_stubs()
     # Import under the reference's own package name.  The product package is
     # called `optimobo_b200`, so there is no clash.

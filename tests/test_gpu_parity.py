@@ -664,8 +664,10 @@ def test_conditioning_proxy_guards_the_fast_mode():
 
 
 def test_fast_mode_operand_format_follows_conditioning():
-    """K3 stores bf16 planes for well-conditioned GPs and scaled fp16 planes (+ direct-difference distances) beyond
-    kappa = 100; both kernel instantiations meet the tolerance inside the guarded range."""
+    """K3 chooses the operand format of the fast mode from the conditioning proxy: "f8c" (fp16 plane + two e4m3
+    correction planes, the CTA-pair kernel) up to kappa = 100, scaled fp16 x3 planes (+ direct-difference distances)
+    beyond; with OMBO_NO_F8C the well-conditioned GPs get bf16 x3 planes.  Every instantiation meets the tolerance
+    inside the guarded range."""
     if not _cabi.fast_path_available():
         pytest.skip("fast path not built")
     rng = np.random.default_rng(5)
@@ -674,7 +676,8 @@ def test_fast_mode_operand_format_follows_conditioning():
         X = rng.random((n, d))
         y = np.sin(3 * X.sum(1))
         gp = ob.GPModel(X, y, ell * np.ones(d), 1.5, device=DEV)
-        assert gp._flags == (2 if gp.conditioning > 100.0 else 0)
+        assert gp._flags == (2 if gp.conditioning > 100.0 else 4)
+        assert gp.plane_format == ("fp16x3" if gp.conditioning > 100.0 else "f8c")
         seen.add(gp._flags)
         assert gp.conditioning < ob.GPModel.FAST_MODE_CONDITIONING_LIMIT
         Xc = rng.random((3000, d))
@@ -683,4 +686,8 @@ def test_fast_mode_operand_format_follows_conditioning():
         mu, var = ob.posterior([gp], Xc, precision="fast")
         np.testing.assert_allclose(mu[0].cpu().numpy(), mu_o, rtol=1e-3, atol=1e-3 * max(1.0, np.abs(mu_o).max()))
         np.testing.assert_allclose(np.sqrt(var[0].cpu().numpy()), np.sqrt(var_o), rtol=1e-3, atol=1e-3 * np.sqrt(1.5))
-    assert seen == {0, 2}
+    assert seen == {2, 4}
+    # d > 12 has no f8c instantiation: bf16 x3 planes
+    X = rng.random((300, 16))
+    gp = ob.GPModel(X, np.sin(X.sum(1)), 2.0 * np.ones(16), 1.0, device=DEV)
+    assert gp.plane_format == ("fp16x3" if gp.conditioning > 100.0 else "bf16x3")

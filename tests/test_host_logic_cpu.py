@@ -131,6 +131,40 @@ def test_allreduce_best_key_gloo_world2():
     assert out[0] == out[1] == (0.75, 4)
 
 
+def _gloo_exact_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    from optimobo_b200.distributed import allgather_best_exact
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    res = []
+    # (a) denormal-range values (late-BO EI, constrained EI x PoF): float32 would flush both to 0 and pick index 3
+    # (b) values that agree to float32 precision but not in FP64   (c) equal values: lowest index   (d) NaN never wins
+    cases = [[(3e-50, 3), (7e-50, 900)], [(1.0 + 1e-12, 50), (1.0, 7)], [(0.75, 9), (0.75, 4)], [(float("nan"), 1), (-2.0, 8)]]
+    for case in cases:
+        v, i = case[rank]
+        pair = torch.tensor([0, i], dtype=torch.int64)
+        pair[:1].view(torch.float64)[0] = v
+        res.append(allgather_best_exact(pair))
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_allgather_best_exact_gloo_world2():
+    """The default multi-rank reduce: one all-gather of the 16-byte (FP64 value, index) pairs, exact for every
+    value range (the packed float32 key is not: ADVICE r1)."""
+    import torch.multiprocessing as mp
+    from optimobo_b200.distributed import pick_best
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_exact_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] == out[1] == [(7e-50, 900), (1.0 + 1e-12, 50), (0.75, 4), (-2.0, 8)]
+    # the packed key really does lose case (a): both float32 images are 0 -> lowest index
+    assert unpack_key(max(pack_key_host(3e-50, 3), pack_key_host(7e-50, 900)))[1] == 3
+    assert pick_best([np.nan, np.nan], [5, 2]) == (-np.inf, 2)
+
+
 # ------------------------------------------------------------------------------------------
 # TuRBO bookkeeping (turbo.py:119-154, :340-380): trust-region length, batch selection
 # ------------------------------------------------------------------------------------------
