@@ -18,10 +18,14 @@
 // and L2 per candidate -- the two limits the single-CTA kernel runs into.
 //   warp 0        B producer (both CTAs): this CTA's rows of the unit's three planes, bytes counted on the leader
 //   warp 1        MMA issuer (leader CTA): per (256-column chunk, 64-deep K-block) 4 x f16 + 2 x 2 x f8f6f4
-//   warp 2        TMEM allocator (512 columns = two 256-column accumulator chunks per CTA)
+//   warp 2        TMEM allocator (512 columns = two 256-column accumulator chunks per CTA), then the candidate
+//                 coordinates of the next tile (counter generator / conversion, scaled and centred)
+//   warp 3        one thread: train slices of the coming K-blocks by TMA bulk copies (ring of 4), copies of the
+//                 generated K* stages to / from the per-CTA cache in L2
 //   warps 4-7     epilogue: tcgen05.ld, square + row sum, var = sigma_f2 - sum V^2 / s^2
 //   warps 8..     K1 generators (8 or 16 warps): distances in FP32 (packed FFMA2), Matern-5/2 / RBF via MUFU,
-//                 fp16 / e4m3 planes written straight into the UMMA operand layouts (SWIZZLE_128B / SWIZZLE_64B)
+//                 fp16 / e4m3 planes written straight into the UMMA operand layouts (SWIZZLE_128B / SWIZZLE_64B);
+//                 no barrier between generator warps inside a tile (mbarrier rings only)
 // L^-1 is lower triangular: chunk c needs K-blocks kb <= 4c+3 only, and on the four diagonal K-blocks of a chunk
 // the rows above the diagonal band are zero, so N shrinks to 192 / 128 / 64 -- in pair mode by letting each CTA
 // fetch a different row range of the band (CTA r loads rows r0 + r N/2 .. of the chunk) and offsetting the
@@ -53,6 +57,14 @@ __device__ __forceinline__ void umma_f8_2sm(uint32_t tmem_d, uint64_t adesc, uin
       : "memory");
 }
 
+#define F8_NSL 4            // train-slice ring depth
+__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};\n" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+
 struct F8Maps {            // tensor maps of the three B planes (128-row and 32-row boxes) and of the K* cache
   CUtensorMap hi128, hi32, c1_128, c1_32, c2_128, c2_32, kc;
 };
@@ -61,9 +73,11 @@ template <int DP, int R, int GW>
 __global__ void __launch_bounds__((8 + GW) * 32, 1)
 k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
   constexpr int NSTA = 3, NSTB = 3;
-  constexpr int GEN_WARPS = GW, GEN_THREADS = GW * 32;
+  constexpr int NSL = F8_NSL;                   // train-slice ring (TMA bulk copies, one slice per fresh K-block)
+  constexpr int GEN_WARPS = GW;
   constexpr int CW = 256, NSLOT = 2, KSH = 2;
-  constexpr int PREP_THREADS = 64;             // warps 2 and 3: candidate coordinates of the NEXT tile
+  constexpr int XT_STRIDE = (DP + 2) * FK;     // floats per slice: DP coordinate rows, sigma_f2 alpha, |b|^2
+  constexpr uint32_t SLICE_BYTES = XT_STRIDE * 4;
   // D = f32, A = B = fp16 / e4m3 (format code 0 in both kinds), K-major, M = 256 (pair); N is patched per unit
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(256 >> 4) << 24);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -104,19 +118,30 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
   unsigned char *sA = fast_smem + ((1024u - (smem_u32(fast_smem) & 1023u)) & 1023u);
   unsigned char *sB = sA + NSTA * STAGE_BYTES;
   float *xc = (float *)(sB + NSTB * STAGE_BYTES);              // [2][DP][128] scaled candidate coords (double buffered)
-  float *xt = xc + 2 * (size_t)DP * FM;                        // [2][(DP+2)][64] train slice (+ alpha, |b|^2 rows)
-  float *mu_sm = xt + 2 * (size_t)(DP + 2) * FK;               // [8][128]
+  float *xt = xc + 2 * (size_t)DP * FM;                        // [NSL][DP + 2][64] train slices
+  float *mu_sm = xt + (size_t)NSL * XT_STRIDE;                 // [2][4][128] mean partials (double buffered by tile)
   uint64_t *bars = (uint64_t *)(((uintptr_t)(mu_sm + 8 * FM) + 15) & ~(uintptr_t)15);
-  uint64_t *a_full = bars, *a_empty = bars + NSTA, *b_full = bars + 2 * NSTA, *b_empty = b_full + NSTB;
-  uint64_t *t_full = b_empty + NSTB, *t_empty = t_full + 4;
-  uint32_t *tmem_slot = (uint32_t *)(t_empty + 4);
-  double *inv_ell = (double *)(bars + 24);
+  uint64_t *a_full = bars, *a_empty = bars + 3, *b_full = bars + 6, *b_empty = bars + 9;
+  uint64_t *t_full = bars + 12, *t_empty = bars + 14;
+  uint64_t *s_full = bars + 16, *s_empty = bars + 20;           // train-slice ring
+  uint64_t *a_written = bars + 24;                              // "all local generator warps have written stage s"
+  uint64_t *xc_full = bars + 27, *xc_empty = bars + 29;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 32);
+  double *inv_ell = (double *)(bars + 34);
 
   if (tid == 0) {
     for (int j = 0; j < DP; ++j) inv_ell[j] = j < d ? 1.0 / prm.gp.ell[j] : 0.0;
-    for (int s = 0; s < NSTA; ++s) { mbar_init(smem_u32(&a_full[s]), 2 * GEN_WARPS); mbar_init(smem_u32(&a_empty[s]), 1); }
+    for (int s = 0; s < NSTA; ++s) {
+      mbar_init(smem_u32(&a_full[s]), 2 * GEN_WARPS);
+      mbar_init(smem_u32(&a_empty[s]), 2);                      // the MMA's commit + this CTA's cache thread
+      mbar_init(smem_u32(&a_written[s]), GEN_WARPS);
+    }
     for (int s = 0; s < NSTB; ++s) { mbar_init(smem_u32(&b_full[s]), 1); mbar_init(smem_u32(&b_empty[s]), 1); }
-    for (int s = 0; s < 4; ++s) { mbar_init(smem_u32(&t_full[s]), 1); mbar_init(smem_u32(&t_empty[s]), 8); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&t_full[s]), 1); mbar_init(smem_u32(&t_empty[s]), 8);
+      mbar_init(smem_u32(&xc_full[s]), 1); mbar_init(smem_u32(&xc_empty[s]), GEN_WARPS);
+    }
+    for (int s = 0; s < NSL; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), GEN_WARPS); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -221,25 +246,95 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
       }
       if (pon) { prm.prof[blockIdx.x * 16 + 2] = w_afull; prm.prof[blockIdx.x * 16 + 3] = w_bfull; prm.prof[blockIdx.x * 16 + 4] = w_tempty; }
     }
-  } else if (warp == 2 || warp == 3) {
+  } else if (warp == 2) {
     // =============================== candidate coordinates of the next tile ===============
     // -2 x the centred, length-scaled coordinates of tile `it` into xc[it & 1] while the generators work on tile
-    // it - 1 (FP64 counter generator / conversion: ~10 k cycles per tile that used to sit on the generators'
-    // critical path).  Named barriers 2 + b ("xc[b] filled") and 4 + b ("xc[b] read").
-    const int pt = tid - 64;
+    // it - 1 (FP64 counter generator / conversion: ~20 k cycles per tile off the generators' critical path).
+    // xc_full[b]: filled (one arrival by this warp), xc_empty[b]: every generator warp has its rows in registers.
     for (long long it = 0; it < n_iter; ++it) {
       const int b = (int)(it & 1);
+      const uint32_t u = (uint32_t)(it >> 1);
       const long long tile = blockIdx.x + it * gridDim.x;
-      if (it >= 2) named_bar_sync(4 + b, PREP_THREADS + GEN_THREADS);
+      if (u > 0) mbar_wait_sleep(smem_u32(&xc_empty[b]), (u - 1) & 1, 64);
       float *xcb = xc + (size_t)b * DP * FM;
-      for (int e = pt; e < FM * DP; e += PREP_THREADS) {
+      for (int e = lane; e < FM * DP; e += 32) {
         const int r_ = e & (FM - 1), j = e >> 7;
         const long long cg = tile * FM + r_;
         xcb[j * FM + r_] = (cg < prm.m && j < d)
                                ? -2.0f * (float)((ombo_pool_coord(prm.pool, cg, j) - prm.gp.center[j]) * inv_ell[j])
                                : 0.f;
       }
-      named_bar_arrive(2 + b, PREP_THREADS + GEN_THREADS);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&xc_full[b]));
+    }
+  } else if (warp == 3) {
+    // =============================== train slices + K* cache (one thread) =================
+    // (a) keeps the ring of train slices NSL - 1 fresh blocks ahead of the generators: DP + 2 bulk copies of 256 B
+    //     (coordinate rows, sigma_f2 alpha, |b|^2 of K-block kb) completing on s_full;
+    // (b) walks the A stages in block order: a FRESH block is copied to the per-CTA cache in L2 once every local
+    //     generator warp has written it (a_written), a CACHED block is streamed back into the stage (2-SM load, bytes
+    //     counted on the leader's a_full together with this CTA's share of the arrivals).  Either way the thread
+    //     then arrives on a_empty: a stage is free once the MMA has consumed it AND the cache copy has read it.
+    if (elect_one()) {
+      long long it_s = 0; int p_s = 0, i_s = 0;
+      bool s_done = n_iter == 0;
+      uint32_t sl = 0, slph = 0;
+      auto slice_next = [&]() {
+        while (!s_done) {
+          const int kb_end = pass_kb_end(p_s), kb_cached = pass_kb_cached(p_s);
+          if (i_s >= kb_end) {
+            i_s = 0;
+            if (++p_s == n_pass) { p_s = 0; if (++it_s == n_iter) s_done = true; }
+            continue;
+          }
+          const int kb = seq_kb(kb_cached, kb_end, i_s++);
+          if (kb < kb_cached) continue;
+          mbar_wait_sleep(smem_u32(&s_empty[sl]), slph ^ 1, 32);
+          const uint32_t full = smem_u32(&s_full[sl]);
+          mbar_expect_tx(full, SLICE_BYTES);
+          const uint32_t dst = smem_u32(xt + (size_t)sl * XT_STRIDE);
+#pragma unroll 1
+          for (int j = 0; j < DP; ++j) bulk_load(dst + j * (FK * 4), prm.gp.xs32 + (size_t)j * np + kb * FK, FK * 4, full);
+          bulk_load(dst + DP * (FK * 4), prm.gp.alpha32 + kb * FK, FK * 4, full);
+          bulk_load(dst + (DP + 1) * (FK * 4), prm.gp.b2_32 + kb * FK, FK * 4, full);
+          if (++sl == NSL) { sl = 0; slph ^= 1; }
+          return;
+        }
+      };
+      for (int k = 0; k < NSL - 1; ++k) slice_next();
+      uint32_t sa = 0, pa = 0;
+      uint32_t wph = 0;                          // a_written completes a phase on FRESH uses of a stage only
+      const uint32_t a_full_leader0 = mapa_rank(smem_u32(&a_full[0]), 0);
+      unsigned char *kc = prm.kcache + (size_t)blockIdx.x * nkb * STAGE_BYTES;
+      for (long long it = 0; it < n_iter; ++it) {
+        for (int p = 0; p < n_pass; ++p) {
+          const int kb_end = pass_kb_end(p), kb_cached = pass_kb_cached(p);
+          const bool store_cache = use_cache && (p + 1 < n_pass);
+          if (kb_cached > 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // earlier passes' stores landed
+          for (int i = 0; i < kb_end; ++i) {
+            const int kb = seq_kb(kb_cached, kb_end, i);
+            const uint32_t stage = smem_u32(sA + sa * STAGE_BYTES);
+            if (kb >= kb_cached) {
+              slice_next();
+              mbar_wait_sleep(smem_u32(&a_written[sa]), (wph >> sa) & 1, 64);
+              wph ^= 1u << sa;
+              if (store_cache) {
+                bulk_store(kc + (size_t)kb * STAGE_BYTES, stage, STAGE_BYTES);
+                asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+              }
+            } else {
+              const uint32_t full_leader = a_full_leader0 + (uint32_t)(sa * 8);
+              mbar_wait_sleep(smem_u32(&a_empty[sa]), pa ^ 1, 32);
+              mbar_expect_tx_remote(full_leader, STAGE_BYTES);
+              mbar_arrive_n_remote(full_leader, GEN_WARPS - 1);
+              tma_load_2d_2sm(stage, &maps.kc, full_leader, 0, (int)((blockIdx.x * nkb + kb) * 256));
+            }
+            mbar_arrive(smem_u32(&a_empty[sa]));
+            if (++sa == NSTA) { sa = 0; pa ^= 1; }
+          }
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
     }
   } else if (warp >= 4 && warp < 8) {
     // =============================== epilogue (both CTAs: own 128 candidates) =============
@@ -277,42 +372,43 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
     }
   } else if (warp >= 8) {
     // =============================== K1 generators ========================================
-    // Warp q (of 8 per row half) owns K columns 8q..8q+7 of the block; lane l owns candidate rows l + 32 rr of
-    // its row half; the candidate coordinates stay in registers for the whole tile.
+    // Warp (qq, rg): K columns 16 qq .. 16 qq + 15 of the block, candidate rows 16 R rg .. 16 R (rg + 1) - 1.
+    // Even lanes own the first 8 of those columns, odd lanes the other 8; a lane pair owns rows r16 + 16 rr
+    // (r16 in 0..15 from the lane bits, see below) whose coordinates stay in registers for the whole tile.  The
+    // lane -> (row, column group) map makes every operand store conflict-free: an STS.128 quarter-warp covers the
+    // eight 16-byte chunks of the SWIZZLE_128B atom, an STS.64 half-warp the sixteen 8-byte slots of two
+    // SWIZZLE_64B rows (an 8-column group alone can only ever reach half of the banks).
+    // Nothing here synchronises the generator warps with each other: slices arrive through a TMA ring, the cache
+    // copy waits on a_written in another warp, the mean is reduced per row group.  Warps that share a scheduler
+    // (same qq) therefore drift apart and overlap their FFMA2, MUFU and conversion phases instead of queueing for
+    // the same pipe in lock-step.
     const int gt = tid - 8 * 32;
-    const int q = (gt >> 5) & 7;
-    const int rh = gt >> 8;                      // row half (GW = 16 only)
+    const int gw = gt >> 5;
+    const int qq = gw & 3, rg = gw >> 2;
+    const int gbit = lane & 1;
+    const int g = 2 * qq + gbit;                   // 8-column group of the K-block
+    const int r16 = ((lane >> 1) & 3) * 2 + ((lane >> 3) & 1) + 8 * (lane >> 4);
+    const int row0 = 16 * R * rg + r16;
+    static_assert(GW * R == 32, "generator rows must cover the tile");
     const bool matern = (prm.gp.kernel == OMBO_KERNEL_MATERN52);
-    constexpr int ROWS = R;                       // rows per lane; R * 32 * (GW / 8) == 128
-    static_assert(R * 32 * (GW / 8) == 128, "generator rows must cover the tile");
-    constexpr int XT_STRIDE = (DP + 2) * FK;
-    uint32_t sa = 0, pa = 0;
-    int xbuf = 0;
-    long long w_aempty = 0;
-    constexpr int LD_ROWS = GEN_THREADS / 16;
-    const int ld_j = gt >> 4, ld_o = (gt & 15) * 4;
-    constexpr int LD_SWEEPS = (DP + 2 + LD_ROWS - 1) / LD_ROWS;
-    auto prefetch_slice = [&](float *dst, int kb) {
+    constexpr int ROWS = R;
+    uint32_t off_hi[ROWS], off_c8[ROWS];
 #pragma unroll
-      for (int sw = 0; sw < LD_SWEEPS; ++sw) {
-        const int jj = ld_j + LD_ROWS * sw;
-        if (jj <= DP + 1) {
-          const float *src = (jj < DP) ? prm.gp.xs32 + (size_t)jj * np + kb * FK + ld_o
-                                       : (jj == DP ? prm.gp.alpha32 : prm.gp.b2_32) + kb * FK + ld_o;
-          const uint32_t sd = smem_u32(dst + jj * FK + ld_o);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(sd), "l"(src) : "memory");
-        }
-      }
-      asm volatile("cp.async.commit_group;\n" ::: "memory");
-    };
-    prefetch_slice(xt, 0);
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
+    for (int rr = 0; rr < ROWS; ++rr) {
+      const int row = row0 + 16 * rr;
+      off_hi[rr] = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((g ^ (row & 7)) & 7) << 4));
+      off_c8[rr] = (uint32_t)((row >> 3) * 512 + (row & 7) * 64 + ((((g >> 1) ^ (row >> 1)) & 3) << 4) + (g & 1) * 8);
+    }
+    const uint32_t sA_u = smem_u32(sA);
+    const uint32_t a_empty_u = smem_u32(a_empty), a_written_u = smem_u32(a_written);
+    const uint32_t s_full_u = smem_u32(s_full), s_empty_u = smem_u32(s_empty);
     const uint32_t a_full_leader0 = mapa_rank(smem_u32(&a_full[0]), 0);
+    uint32_t sa = 0, pa = 0, sl = 0, slph = 0;
+    if (prm.dbg & 8) __nanosleep(400u * (unsigned)rg);       // experiment: start the row groups out of phase
     for (long long it = 0; it < n_iter; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
       const int b = (int)(it & 1);
-      named_bar_sync(2 + b, PREP_THREADS + GEN_THREADS);       // xc[b] holds this tile
+      mbar_wait_sleep(smem_u32(&xc_full[b]), (uint32_t)(it >> 1) & 1, 64);     // xc[b] holds this tile
       const float *xcb = xc + (size_t)b * DP * FM;
       float mu_acc[ROWS];
       float x[ROWS][DP], a2[ROWS];
@@ -321,54 +417,39 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
         float acc = 0.f;
         mu_acc[rr] = 0.f;
 #pragma unroll
-        for (int j = 0; j < DP; ++j) { x[rr][j] = xcb[j * FM + lane + 32 * (ROWS * rh + rr)]; acc = fmaf(x[rr][j], x[rr][j], acc); }
+        for (int j = 0; j < DP; ++j) { x[rr][j] = xcb[j * FM + row0 + 16 * rr]; acc = fmaf(x[rr][j], x[rr][j], acc); }
         a2[rr] = 0.25f * acc;
       }
-      if (it + 2 < n_iter) named_bar_arrive(4 + b, PREP_THREADS + GEN_THREADS);   // xc[b] may be refilled
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&xc_empty[b]));                   // xc[b] may be refilled
       for (int p = 0; p < n_pass; ++p) {
         const int kb_end = pass_kb_end(p), kb_cached = pass_kb_cached(p);
-        const bool store_cache = use_cache && (p + 1 < n_pass);
-        unsigned char *kc = prm.kcache + (size_t)blockIdx.x * nkb * STAGE_BYTES;
-        if (kb_cached > 0 && gt == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // stores landed
         for (int i = 0; i < kb_end; ++i) {
           const int kb = seq_kb(kb_cached, kb_end, i);
-          const uint32_t full_leader = a_full_leader0 + (uint32_t)(sa * 8);
           if (kb < kb_cached) {
-            // a K* block of an earlier pass: one thread streams the cached 32 KB stage back (2-SM load: the bytes are
-            // counted on the leader's barrier) and performs all of this CTA's arrivals.  EVERY generator thread waits
-            // for the stage's release first: a warp that skipped ahead through a run of cached blocks would get more
-            // than one barrier phase ahead of the MMA, and a parity wait cannot tell phases two apart.
-            if (gt == 0) {
-              // a cache store issued from this stage three blocks ago must have finished reading it
-              if (store_cache) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-              mbar_wait_prof(smem_u32(&a_empty[sa]), pa ^ 1, 32, w_aempty, pon);
-              mbar_expect_tx_remote(full_leader, STAGE_BYTES);
-              mbar_arrive_n_remote(full_leader, GEN_WARPS - 1);
-              tma_load_2d_2sm(smem_u32(sA + sa * STAGE_BYTES), &maps.kc, full_leader, 0, (int)((blockIdx.x * nkb + kb) * 256));
-            } else {
-              mbar_wait_sleep(smem_u32(&a_empty[sa]), pa ^ 1, 128);
-            }
-            __syncwarp();
+            // a K* block of an earlier pass (reloaded by warp 3).  Every generator warp still waits for the stage's
+            // release: a warp that skipped ahead through a run of cached blocks would get more than one barrier
+            // phase ahead of the MMA, and a parity wait cannot tell phases two apart.
+            mbar_wait_sleep(a_empty_u + sa * 8, pa ^ 1, 128);
             if (++sa == NSTA) { sa = 0; pa ^= 1; }
             continue;
           }
-          // with the cache every block is generated once per tile, otherwise the mean is taken in the last pass
-          const bool do_mu = use_cache || (p == n_pass - 1);
-          // the next block this CTA generates (fresh blocks come in increasing order; across passes / tiles it wraps)
-          prefetch_slice(xt + (xbuf ^ 1) * XT_STRIDE, (kb + 1 < kb_end) ? kb + 1 : (p + 1 < n_pass ? pass_kb_cached(p + 1) : 0));
-          const float *xs = xt + xbuf * XT_STRIDE + 8 * q;
-          unsigned char *st_hi = sA + sa * STAGE_BYTES;
-          float2 r2[ROWS][4];
+          mbar_wait_sleep(s_full_u + sl * 8, slph, 20);                       // this block's train slice has landed
+          const float *xs = xt + sl * XT_STRIDE + 8 * g;
+          const uint32_t st_u = sA_u + sa * STAGE_BYTES;
           if (!(prm.dbg & 2)) {
-            const float4 n0 = *(const float4 *)(xs + (DP + 1) * FK);      // |b_i|^2
-            const float4 n1 = *(const float4 *)(xs + (DP + 1) * FK + 4);
+            float2 r2[ROWS][4];
+            {
+              const float4 n0 = *(const float4 *)(xs + (DP + 1) * FK);      // |b_i|^2
+              const float4 n1 = *(const float4 *)(xs + (DP + 1) * FK + 4);
 #pragma unroll
-            for (int rr = 0; rr < ROWS; ++rr) {
-              const float2 aa = make_float2(a2[rr], a2[rr]);
-              r2[rr][0] = __fadd2_rn(aa, make_float2(n0.x, n0.y));
-              r2[rr][1] = __fadd2_rn(aa, make_float2(n0.z, n0.w));
-              r2[rr][2] = __fadd2_rn(aa, make_float2(n1.x, n1.y));
-              r2[rr][3] = __fadd2_rn(aa, make_float2(n1.z, n1.w));
+              for (int rr = 0; rr < ROWS; ++rr) {
+                const float2 aa = make_float2(a2[rr], a2[rr]);
+                r2[rr][0] = __fadd2_rn(aa, make_float2(n0.x, n0.y));
+                r2[rr][1] = __fadd2_rn(aa, make_float2(n0.z, n0.w));
+                r2[rr][2] = __fadd2_rn(aa, make_float2(n1.x, n1.y));
+                r2[rr][3] = __fadd2_rn(aa, make_float2(n1.z, n1.w));
+              }
             }
 #pragma unroll
             for (int j = 0; j < DP; ++j) {
@@ -383,98 +464,89 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
                 r2[rr][3] = __ffma2_rn(xx, make_float2(t1.z, t1.w), r2[rr][3]);
               }
             }
+            const float4 al0 = *(const float4 *)(xs + DP * FK);
+            const float4 al1 = *(const float4 *)(xs + DP * FK + 4);
+            mbar_wait_sleep(a_empty_u + sa * 8, pa ^ 1, 32);                   // stage released (MMA + cache copy)
+#pragma unroll
+            for (int rr = 0; rr < ROWS; ++rr) {
+              float2 kv[4];
+              if (matern) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  float2 rad, ex;
+                  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad.x) : "f"(fabsf(r2[rr][e].x)));
+                  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad.y) : "f"(fabsf(r2[rr][e].y)));
+                  const float2 arg = __fmul2_rn(rad, make_float2(-3.2259955597f, -3.2259955597f));   // -sqrt5 log2(e)
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.x) : "f"(arg.x));
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.y) : "f"(arg.y));
+                  const float2 poly = __ffma2_rn(rad, make_float2(2.2360679775f, 2.2360679775f),
+                                                 __ffma2_rn(r2[rr][e], make_float2(1.6666666667f, 1.6666666667f),
+                                                            make_float2(1.0f, 1.0f)));
+                  kv[e] = __fmul2_rn(poly, ex);
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 arg = __fmul2_rn(r2[rr][e], make_float2(-0.7213475204f, -0.7213475204f));  // -0.5 log2(e)
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(kv[e].x) : "f"(arg.x));
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(kv[e].y) : "f"(arg.y));
+                }
+              }
+              {
+                float2 m2 = __fmul2_rn(kv[0], make_float2(al0.x, al0.y));
+                m2 = __ffma2_rn(kv[1], make_float2(al0.z, al0.w), m2);
+                m2 = __ffma2_rn(kv[2], make_float2(al1.x, al1.y), m2);
+                m2 = __ffma2_rn(kv[3], make_float2(al1.z, al1.w), m2);
+                mu_acc[rr] += m2.x + m2.y;
+              }
+              uint32_t hi[4];
+              uint32_t c1[2], c2[2];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __half2 h = __float22half2_rn(kv[e]);
+                const float2 hf = __half22float2(h);
+                // 2^12 (k' - hi): the residual is exact in FP32, the scaling too
+                const float2 res = __ffma2_rn(hf, make_float2(-4096.0f, -4096.0f), __fmul2_rn(kv[e], make_float2(4096.0f, 4096.0f)));
+                hi[e] = *reinterpret_cast<const uint32_t *>(&h);
+                const uint32_t l8 = (uint32_t)__nv_cvt_float2_to_fp8x2(res, __NV_SATFINITE, __NV_E4M3);
+                const uint32_t a8 = (uint32_t)__nv_cvt_float2_to_fp8x2(hf, __NV_SATFINITE, __NV_E4M3);
+                if (e & 1) { c1[e >> 1] |= l8 << 16; c2[e >> 1] |= a8 << 16; }
+                else { c1[e >> 1] = l8; c2[e >> 1] = a8; }
+              }
+              sts128(st_u + off_hi[rr], hi[0], hi[1], hi[2], hi[3]);
+              sts64(st_u + F8_OFF_C1 + off_c8[rr], c1[0], c1[1]);
+              sts64(st_u + F8_OFF_C2 + off_c8[rr], c2[0], c2[1]);
+            }
           } else {
-#pragma unroll
-            for (int rr = 0; rr < ROWS; ++rr)
-#pragma unroll
-              for (int e = 0; e < 4; ++e) r2[rr][e] = make_float2(1.f, 1.f);
-          }
-          const float4 al0 = *(const float4 *)(xs + DP * FK);
-          const float4 al1 = *(const float4 *)(xs + DP * FK + 4);
-          mbar_wait_prof(smem_u32(&a_empty[sa]), pa ^ 1, 32, w_aempty, pon);   // stage released by the MMA
-#pragma unroll
-          for (int rr = 0; rr < ROWS; ++rr) {
-            float2 kv[4];
-            if (prm.dbg & 2) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) kv[e] = r2[rr][e];
-            } else if (matern) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float2 rad, ex;
-                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad.x) : "f"(fabsf(r2[rr][e].x)));
-                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad.y) : "f"(fabsf(r2[rr][e].y)));
-                const float2 arg = __fmul2_rn(rad, make_float2(-3.2259955597f, -3.2259955597f));   // -sqrt5 log2(e)
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.x) : "f"(arg.x));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex.y) : "f"(arg.y));
-                const float2 poly = __ffma2_rn(rad, make_float2(2.2360679775f, 2.2360679775f),
-                                               __ffma2_rn(r2[rr][e], make_float2(1.6666666667f, 1.6666666667f),
-                                                          make_float2(1.0f, 1.0f)));
-                kv[e] = __fmul2_rn(poly, ex);
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 arg = __fmul2_rn(r2[rr][e], make_float2(-0.7213475204f, -0.7213475204f));  // -0.5 log2(e)
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(kv[e].x) : "f"(arg.x));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(kv[e].y) : "f"(arg.y));
-              }
-            }
-            if (do_mu) {
-              float2 m2 = __fmul2_rn(kv[0], make_float2(al0.x, al0.y));
-              m2 = __ffma2_rn(kv[1], make_float2(al0.z, al0.w), m2);
-              m2 = __ffma2_rn(kv[2], make_float2(al1.x, al1.y), m2);
-              m2 = __ffma2_rn(kv[3], make_float2(al1.z, al1.w), m2);
-              mu_acc[rr] += m2.x + m2.y;
-            }
-            uint32_t hi[4];
-            uint32_t c1[2], c2[2];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const __half2 h = __float22half2_rn(kv[e]);
-              const float2 hf = __half22float2(h);
-              // 2^12 (k' - hi): the residual is exact in FP32, the scaling too
-              const float2 res = __ffma2_rn(hf, make_float2(-4096.0f, -4096.0f), __fmul2_rn(kv[e], make_float2(4096.0f, 4096.0f)));
-              hi[e] = *reinterpret_cast<const uint32_t *>(&h);
-              const uint32_t l8 = (uint32_t)__nv_cvt_float2_to_fp8x2(res, __NV_SATFINITE, __NV_E4M3);
-              const uint32_t a8 = (uint32_t)__nv_cvt_float2_to_fp8x2(hf, __NV_SATFINITE, __NV_E4M3);
-              if (e & 1) { c1[e >> 1] |= l8 << 16; c2[e >> 1] |= a8 << 16; }
-              else { c1[e >> 1] = l8; c2[e >> 1] = a8; }
-            }
-            const int row = lane + 32 * (ROWS * rh + rr);
-            const uint32_t off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((q ^ (row & 7)) & 7) << 4));
-            *(uint4 *)(st_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            const uint32_t off8 = (uint32_t)((row >> 3) * 512 + (row & 7) * 64 + ((((q >> 1) ^ (row >> 1)) & 3) << 4) + (q & 1) * 8);
-            *(uint2 *)(st_hi + F8_OFF_C1 + off8) = make_uint2(c1[0], c1[1]);
-            *(uint2 *)(st_hi + F8_OFF_C2 + off8) = make_uint2(c2[0], c2[1]);
+            mbar_wait_sleep(a_empty_u + sa * 8, pa ^ 1, 32);
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive_remote(full_leader);            // the leader's MMA consumes both halves
-          const uint32_t stage_just_written = smem_u32(sA + sa * STAGE_BYTES);
+          if (lane == 0) {
+            mbar_arrive(s_empty_u + sl * 8);                                   // slice free
+            mbar_arrive_remote(a_full_leader0 + sa * 8);                       // the leader's MMA consumes both halves
+            mbar_arrive(a_written_u + sa * 8);                                 // this CTA's cache copy may start
+          }
           if (++sa == NSTA) { sa = 0; pa ^= 1; }
-          asm volatile("cp.async.wait_group 0;\n" ::: "memory");          // next slice has landed
-          if (store_cache && gt == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-          asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
-          if (store_cache && gt == 0) bulk_store(kc + (size_t)kb * STAGE_BYTES, stage_just_written, STAGE_BYTES);
-          xbuf ^= 1;
+          if (++sl == NSL) { sl = 0; slph ^= 1; }
         }
       }
-      if (pon && gt == 0) prm.prof[blockIdx.x * 16 + 5] = w_aempty;
-      // mean: one partial sum per (chunk warp, row)
+      // mean: lane pairs hold the two column groups of a row, the four warps of a row group the four column pairs
+      float *mub = mu_sm + (size_t)b * 4 * FM;
 #pragma unroll
-      for (int rr = 0; rr < ROWS; ++rr) mu_sm[q * FM + lane + 32 * (ROWS * rh + rr)] = mu_acc[rr];
-      asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));
-      if (gt < FM) {
-        const long long cg = tile * FM + gt;
-        if (cg < prm.m) {
-          float acc = 0.f;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) acc += mu_sm[w * FM + gt];
-          prm.mu_out[cg] = (double)acc;
-        }
+      for (int rr = 0; rr < ROWS; ++rr) {
+        const float m = mu_acc[rr] + __shfl_xor_sync(0xffffffffu, mu_acc[rr], 1);
+        if (!gbit) mub[qq * FM + row0 + 16 * rr] = m;
       }
-      asm volatile("bar.sync 1, %0;\n" ::"n"(GEN_THREADS));       // mu_sm is rewritten by the next tile
+      named_bar_sync(1 + rg, 128);
+      const int tg = qq * 32 + lane;
+      if (tg < 16 * R) {
+        const int row = 16 * R * rg + tg;
+        const long long cg = tile * FM + row;
+        if (cg < prm.m) prm.mu_out[cg] = (double)((mub[row] + mub[FM + row]) + (mub[2 * FM + row] + mub[3 * FM + row]));
+      }
+      // mu_sm is double buffered by tile: the rows of buffer b are rewritten two tiles later, after the next
+      // tile's barrier of the same row group
     }
   }
 
@@ -503,8 +575,8 @@ static int make_plane_map(CUtensorMap *map, const void *base, int n_pad, int esz
 
 template <int DP, int R, int GW>
 static int launch_fast8(ombo_ctx *ctx, const F8Maps &maps, const FastParams &prm, int grid, cudaStream_t s) {
-  const size_t smem = (size_t)6 * STAGE_BYTES + 2 * (size_t)DP * FM * 4 + 2 * (size_t)(DP + 2) * FK * 4 +
-                      8 * FM * 4 + 16 + 24 * 8 + 32 * 8 + 1024;
+  const size_t smem = (size_t)6 * STAGE_BYTES + 2 * (size_t)DP * FM * 4 + (size_t)F8_NSL * (DP + 2) * FK * 4 +
+                      8 * FM * 4 + 16 + 34 * 8 + 16 * 8 + 1024;
   // per device, not per process: the attribute belongs to the (function, device) pair
   OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast8<DP, R, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(ctx, s);
