@@ -60,7 +60,7 @@ int ombo_ctx_create(int device, ombo_ctx **out) {
     k.fast_mode = geti("OMBO_FAST_MODE", 0);
     k.fast_cluster = geti("OMBO_FAST_CLUSTER", 1);
     k.fast_dbg = geti("OMBO_FAST_DBG", 0);
-    k.fast_profile = getenv("OMBO_FAST_PROFILE") != nullptr;
+    k.fast_profile = geti("OMBO_FAST_PROFILE", 0);
     k.fast_notrim = getenv("OMBO_FAST_NOTRIM") != nullptr;
     k.fast_nocache = getenv("OMBO_FAST_NOCACHE") != nullptr;
     k.fast_zerocache = getenv("OMBO_FAST_ZEROCACHE") != nullptr;

@@ -65,6 +65,25 @@ __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};\n" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
 
+#define F8_TRACE_N 8192
+#ifndef F8_TRACING
+#define F8_TRACING 0      // build with EXTRA=-DF8_TRACING=1 and run with OMBO_FAST_PROFILE=2 (scripts/trace_fast8.py)
+#endif
+// event trace (timing experiments): CTA 0 only, tiles 2 and 3, one region per role
+#if !F8_TRACING
+#define F8_TRACE(role, code) do { } while (0)
+#define F8_TRACE_G(code) do { } while (0)
+#define F8_TRACE_E(code) do { } while (0)
+#else
+#define F8_TRACE_G(code) do { if (trole >= 0) F8_TRACE(trole, code); } while (0)
+#define F8_TRACE_E(code) do { if (warp == 4 && lane == 0) F8_TRACE(4, code); } while (0)
+#define F8_TRACE(role, code)                                                                   \
+  do {                                                                                         \
+    if (tron && it >= 2 && it < 4 && tr_n[role] < F8_TRACE_N)                                  \
+      prm.trace[(role) * F8_TRACE_N + tr_n[role]++] = (clock64() << 8) | (long long)(code);    \
+  } while (0)
+#endif
+
 struct F8Maps {            // tensor maps of the three B planes (128-row and 32-row boxes) and of the K* cache
   CUtensorMap hi128, hi32, c1_128, c1_32, c2_128, c2_32, kc;
 };
@@ -154,7 +173,16 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const bool pon = prm.prof != nullptr;
-
+#if F8_TRACING
+  const bool tron = prm.trace != nullptr && blockIdx.x == 0;
+  int tr_n[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+  // 24 warps leave 80 registers per thread, which the generator loop does not fit in (it spilled and re-derived
+  // its addresses every K-block).  The four role warps and the epilogue give registers back, the generator
+  // warpgroups take them: the pool is what the CTA was launched with, 768 x 80 = 128 x 56 + 128 x 72 + 512 x 88.
+  // (the role code of a warpgroup has to sit behind ITS setmaxnreg for ptxas to allocate by the new limit)
+  if (warp < 4) {
+  if (GW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
   if (warp == 0) {
     // =============================== B producer (both CTAs) ===============================
     if (elect_one()) {
@@ -170,6 +198,7 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
               const int ncols = unit_ncols(c, kb), rows = ncols >> 1;          // rows of the band this CTA holds
               const int row0 = c * CW + unit_r0(c, kb) + (int)crank * rows;
               mbar_wait_prof(smem_u32(&b_empty[st]), ph ^ 1, 64, w_bempty, pon);
+              F8_TRACE(0, kb * 8 + c);
               const uint32_t dst = smem_u32(sB + st * STAGE_BYTES);
               // the leader alone arms its barrier, with the bytes of BOTH halves (256 B per band row over the planes)
               const uint32_t full = mapa_rank(smem_u32(&b_full[st]), 0);
@@ -205,7 +234,9 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
           for (int c = c_first; c <= c_last; ++c) lastp[c - c_first] = last_pos(kb_cached, kb_end, c);
           for (int i = 0; i < kb_end; ++i) {
             const int kb = seq_kb(kb_cached, kb_end, i);
+            F8_TRACE(1, 0x80 | kb);
             mbar_wait_prof(smem_u32(&a_full[sa]), pa, MMA_SLEEP_NS, w_afull, pon);
+            F8_TRACE(1, 0xC0 | kb);
             tc_fence_after();
             const uint32_t a_hi = smem_u32(sA + sa * STAGE_BYTES);
             for (int c = max(c_first, kb >> KSH); c <= c_last; ++c) {
@@ -220,6 +251,7 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
               const uint32_t dcol = tmem_base + (uint32_t)(slot * CW + r0);
               const uint32_t idesc = IDESC | ((uint32_t)(ncols >> 3) << 17);
               mbar_wait_prof(smem_u32(&b_full[sb]), pb, MMA_SLEEP_NS, w_bfull, pon);
+              F8_TRACE(1, kb * 4 + (c & 3));
               tc_fence_after();
               const uint32_t b_hi = smem_u32(sB + sb * STAGE_BYTES);
               if (!(prm.dbg & 1)) {
@@ -240,6 +272,7 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
               if (++sb == NSTB) { sb = 0; pb ^= 1; }
             }
             umma_commit_2sm(smem_u32(&a_empty[sa]));
+            F8_TRACE(1, 0x40 | kb);
             if (++sa == NSTA) { sa = 0; pa ^= 1; }
           }
         }
@@ -317,6 +350,7 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
             if (kb >= kb_cached) {
               slice_next();
               mbar_wait_sleep(smem_u32(&a_written[sa]), (wph >> sa) & 1, 64);
+              F8_TRACE(3, kb);
               wph ^= 1u << sa;
               if (store_cache) {
                 bulk_store(kc + (size_t)kb * STAGE_BYTES, stage, STAGE_BYTES);
@@ -325,18 +359,22 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
             } else {
               const uint32_t full_leader = a_full_leader0 + (uint32_t)(sa * 8);
               mbar_wait_sleep(smem_u32(&a_empty[sa]), pa ^ 1, 32);
+              F8_TRACE(3, 0x40 | kb);
               mbar_expect_tx_remote(full_leader, STAGE_BYTES);
               mbar_arrive_n_remote(full_leader, GEN_WARPS - 1);
               tma_load_2d_2sm(stage, &maps.kc, full_leader, 0, (int)((blockIdx.x * nkb + kb) * 256));
             }
             mbar_arrive(smem_u32(&a_empty[sa]));
+            F8_TRACE(3, 0x80 | kb);
             if (++sa == NSTA) { sa = 0; pa ^= 1; }
           }
         }
       }
       asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
     }
-  } else if (warp >= 4 && warp < 8) {
+  }
+  } else if (warp < 8) {
+    if (GW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
     // =============================== epilogue (both CTAs: own 128 candidates) =============
     const int quad = warp - 4;
     const int row = quad * 32 + lane;
@@ -348,10 +386,12 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
       for (int c = 0; c < n_chunks; ++c) {
         const int slot = c & (NSLOT - 1);
         mbar_wait_sleep(smem_u32(&t_full[slot]), (fph >> slot) & 1, 200);
+        F8_TRACE_E(c);
         fph ^= (1u << slot);
         tc_fence_after();
         float part[4] = {0.f, 0.f, 0.f, 0.f};
         const int ncw = min(CW, np - c * CW);
+#pragma unroll 1
         for (int q = 0; q < ncw / 32; ++q) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * CW + q * 32), v);
@@ -362,6 +402,7 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(t_empty_leader + (uint32_t)(slot * 8));
+        F8_TRACE_E(0x40 | c);
         ss += (double)((part[0] + part[1]) + (part[2] + part[3]));
       }
       const long long cg = tile * FM + row;
@@ -370,7 +411,8 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
         prm.var_out[cg] = fmax(v, prm.gp.var_floor) + prm.gp.sigma_n2;
       }
     }
-  } else if (warp >= 8) {
+  } else {
+    if (GW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;\n");
     // =============================== K1 generators ========================================
     // Warp (qq, rg): K columns 16 qq .. 16 qq + 15 of the block, candidate rows 16 R rg .. 16 R (rg + 1) - 1.
     // Even lanes own the first 8 of those columns, odd lanes the other 8; a lane pair owns rows r16 + 16 rr
@@ -404,6 +446,9 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
     const uint32_t s_full_u = smem_u32(s_full), s_empty_u = smem_u32(s_empty);
     const uint32_t a_full_leader0 = mapa_rank(smem_u32(&a_full[0]), 0);
     uint32_t sa = 0, pa = 0, sl = 0, slph = 0;
+#if F8_TRACING
+    const int trole = (lane == 0) ? (gw == 0 ? 5 : (gw == 5 ? 6 : (gw == GW - 1 ? 7 : -1))) : -1;
+#endif
     if (prm.dbg & 8) __nanosleep(400u * (unsigned)rg);       // experiment: start the row groups out of phase
     for (long long it = 0; it < n_iter; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
@@ -434,7 +479,9 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
             if (++sa == NSTA) { sa = 0; pa ^= 1; }
             continue;
           }
+          F8_TRACE_G(kb);
           mbar_wait_sleep(s_full_u + sl * 8, slph, 20);                       // this block's train slice has landed
+          F8_TRACE_G(0x40 | kb);
           const float *xs = xt + sl * XT_STRIDE + 8 * g;
           const uint32_t st_u = sA_u + sa * STAGE_BYTES;
           if (!(prm.dbg & 2)) {
@@ -466,7 +513,9 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
             }
             const float4 al0 = *(const float4 *)(xs + DP * FK);
             const float4 al1 = *(const float4 *)(xs + DP * FK + 4);
+            F8_TRACE_G(0x80 | kb);
             mbar_wait_sleep(a_empty_u + sa * 8, pa ^ 1, 32);                   // stage released (MMA + cache copy)
+            F8_TRACE_G(0xC0 | kb);
 #pragma unroll
             for (int rr = 0; rr < ROWS; ++rr) {
               float2 kv[4];
@@ -522,6 +571,7 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
           }
           fence_proxy_async_smem();
           __syncwarp();
+          F8_TRACE_G(0x20 | kb);
           if (lane == 0) {
             mbar_arrive(s_empty_u + sl * 8);                                   // slice free
             mbar_arrive_remote(a_full_leader0 + sa * 8);                       // the leader's MMA consumes both halves
@@ -614,6 +664,13 @@ int ombo_posterior_fast8(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lo
   const bool want_prof = ctx->knobs.fast_profile != 0;
   if (want_prof && !ctx->prof_dev) OMBO_CUDA(cudaMalloc(&ctx->prof_dev, 16 * 256 * sizeof(long long)));
   prm.prof = want_prof ? ctx->prof_dev : nullptr;
+  prm.trace = nullptr;
+  static long long *trace_dev = nullptr;
+  if (ctx->knobs.fast_profile == 2) {
+    if (!trace_dev) OMBO_CUDA(cudaMalloc(&trace_dev, 8 * F8_TRACE_N * sizeof(long long)));
+    OMBO_CUDA(cudaMemsetAsync(trace_dev, 0, 8 * F8_TRACE_N * sizeof(long long), s));
+    prm.trace = trace_dev;
+  }
   if (want_prof) OMBO_CUDA(cudaMemsetAsync(ctx->prof_dev, 0, 16 * 256 * sizeof(long long), s));
   int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
   grid = (grid + 1) / 2 * 2;                    // whole pairs; a surplus CTA runs a dummy tile
@@ -645,6 +702,18 @@ int ombo_posterior_fast8(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lo
     OMBO_CUDA(cudaMemcpy(h, ctx->prof_dev, sizeof(h), cudaMemcpyDeviceToHost));
     double a[8] = {0};
     for (int b = 0; b < grid; ++b) for (int k = 0; k < 8; ++k) a[k] += (double)h[b * 16 + k] / grid;
+    if (prm.trace) {
+      static long long ht[8 * F8_TRACE_N];
+      OMBO_CUDA(cudaMemcpy(ht, prm.trace, sizeof(ht), cudaMemcpyDeviceToHost));
+      const char *path = getenv("OMBO_FAST_TRACE_FILE");
+      FILE *f = fopen(path ? path : "gpurun_out/fast8_trace.txt", "w");
+      if (f) {
+        for (int r = 0; r < 8; ++r)
+          for (int e = 0; e < F8_TRACE_N && ht[r * F8_TRACE_N + e]; ++e)
+            fprintf(f, "%d %lld %lld\n", r, ht[r * F8_TRACE_N + e] >> 8, ht[r * F8_TRACE_N + e] & 255);
+        fclose(f);
+      }
+    }
     fprintf(stderr, "[fast8 prof] per-CTA cycles (leader + peer averaged): tma.wait_b_empty %.0f / tma.total %.0f | mma.wait_a_full %.0f "
             "wait_b_full %.0f wait_t_empty %.0f | gen.wait_a_empty %.0f  (tiles/CTA %.1f)\n",
             a[0], a[1], 2 * a[2], 2 * a[3], 2 * a[4], a[5], (double)tiles / grid);

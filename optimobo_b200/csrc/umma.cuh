@@ -231,6 +231,7 @@ struct FastParams {
   int mean_only;     // 1: this GP's variance is not read by the acquisition -> K1 + mean only, no MMA
   int trim_b;        // 1: map_kc holds 64-row boxes of both B planes; diagonal K-blocks fetch only the rows they multiply
   int dbg;   // bit 0: skip the MMAs, bit 1: skip the K1 math (timing experiments only; results are garbage)
+  long long *trace;  // optional event trace of CTA 0 (OMBO_FAST_PROFILE=2): [8 roles][F8_TRACE_N] of (clock << 8 | code)
 };
 
 
