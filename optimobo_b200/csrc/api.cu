@@ -65,7 +65,9 @@ int ombo_ctx_create(int device, ombo_ctx **out) {
     k.fast_nocache = getenv("OMBO_FAST_NOCACHE") != nullptr;
     k.fast_zerocache = getenv("OMBO_FAST_ZEROCACHE") != nullptr;
     k.fast_mean_in_main = getenv("OMBO_FAST_MEAN_IN_MAIN") != nullptr;
-    k.fast_gen_warps = geti("OMBO_FAST_GEN_WARPS", 16);
+    k.fast_gen_warps = geti("OMBO_FAST_GEN_WARPS", 8);
+    k.f8_max_run = geti("OMBO_F8_MAXRUN", 0);
+    { const char *e = getenv("OMBO_F8_TG"); k.f8_tg = e ? atof(e) : 3.0; }
     k.no_f8c = getenv("OMBO_NO_F8C") != nullptr;
     { const char *e = getenv("OMBO_F8C_KAPPA"); k.f8c_kappa = e ? atof(e) : OMBO_F8C_KAPPA_DEFAULT; }
     k.acq_fp64 = getenv("OMBO_ACQ_FP64") != nullptr;
@@ -95,6 +97,7 @@ int ombo_ctx_destroy(ombo_ctx *c) {
   }
   if (c->prof_ev[0]) for (int i = 0; i < 2 * OMBO_PROF_MAX; ++i) cudaEventDestroy(c->prof_ev[i]);
   if (c->prof_dev) cudaFree(c->prof_dev);
+  if (c->f8_sched) cudaFree(c->f8_sched);
   if (c->ws_best) cudaFree(c->ws_best);
   if (c->pinned_best) cudaFreeHost(c->pinned_best);
   cudaStreamDestroy(c->copy_stream);

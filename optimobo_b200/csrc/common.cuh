@@ -43,7 +43,9 @@ struct ombo_knobs {
   int fast_dbg;           // OMBO_FAST_DBG: timing experiments (results are garbage)
   int fast_profile;       // OMBO_FAST_PROFILE: per-CTA wait-cycle counters printed to stderr
   int fast_notrim, fast_nocache, fast_zerocache, fast_mean_in_main;
-  int fast_gen_warps;     // OMBO_FAST_GEN_WARPS: 8 or 16 K1 generator warps in the f8c kernel
+  int fast_gen_warps;     // OMBO_FAST_GEN_WARPS: 8 (default) or 16 K1 generator warps in the f8c kernel
+  int f8_max_run;         // OMBO_F8_MAXRUN: most reload steps in a row between two generated blocks
+  double f8_tg;           // OMBO_F8_TG: generator time per K-block in units of one 256-column MMA unit (schedule)
   int no_f8c;             // OMBO_NO_F8C: never choose the fp16 + 2 x e4m3 operand format
   double f8c_kappa;       // OMBO_F8C_KAPPA: conditioning limit of that format
   int acq_fp64;           // OMBO_ACQ_FP64: keep the FP64 acquisition kernel in fast mode
@@ -55,6 +57,8 @@ struct ombo_ctx {
   int64_t launches;
   ombo_knobs knobs;
   long long *prof_dev;    // per-CTA wait counters of the fast kernels (OMBO_FAST_PROFILE)
+  // step schedule of the f8c kernel (posterior_fast8.cu), rebuilt when n_pad changes
+  unsigned int *f8_sched; int f8_sched_np, f8_sched_len, f8_sched_cap;
   // workspaces (grown on demand, freed in ctx_destroy)
   void *ws_post;      size_t ws_post_bytes;      // posterior mu/var chunk buffers
   void *ws_scratch;   size_t ws_scratch_bytes;   // FP64 K* tiles (L2 resident) / fast-path scratch

@@ -29,9 +29,16 @@
 // L^-1 is lower triangular: chunk c needs K-blocks kb <= 4c+3 only, and on the four diagonal K-blocks of a chunk
 // the rows above the diagonal band are zero, so N shrinks to 192 / 128 / 64 -- in pair mode by letting each CTA
 // fetch a different row range of the band (CTA r loads rows r0 + r N/2 .. of the chunk) and offsetting the
-// accumulator columns by r0.  TMEM holds two chunks; n_pad > 512 takes several passes with the K* blocks of
-// earlier passes streamed back from a per-CTA cache in L2 (as in posterior_fast.cu).
+// accumulator columns by r0.
+// TMEM holds two 256-column accumulators ("slots"); a tile with more chunks walks a STEP SCHEDULE built on the host
+// (f8_build_schedule): every K-block is generated exactly once, in order, and multiplied into the chunks open at
+// that moment; a chunk that opens later (when a slot has been drained) gets the blocks it missed streamed back from
+// a per-CTA cache in L2, and those reload steps are placed where the tensor core would otherwise wait for the
+// generators (K1 costs ~3 units of MMA time per block).  All roles walk the same schedule, one 32-bit word per step.
 #include <cuda_fp8.h>
+
+#include <deque>
+#include <vector>
 
 #include "umma.cuh"
 
@@ -61,6 +68,14 @@ __device__ __forceinline__ void umma_f8_2sm(uint32_t tmem_d, uint64_t adesc, uin
 __device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
+__device__ __forceinline__ void st_release_shared(uint32_t a, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;\n" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
 __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};\n" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
@@ -84,6 +99,14 @@ __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
   } while (0)
 #endif
 
+// schedule word: one step = one K-block (fresh: generated now / cached: reloaded) multiplied into <= 2 chunks
+#define SW_KB(w) ((int)((w) & 0xFFu))
+#define SW_FRESH(w) (((w) >> 8) & 1u)
+#define SW_STORE(w) (((w) >> 9) & 1u)                            // fresh block that a later chunk reloads
+#define SW_CHUNK(w, slot) ((int)(((w) >> (10 + 6 * (slot))) & 63u) - 1)   // chunk in TMEM slot 0 / 1, -1 = none
+#define SW_FIRST(w, slot) (((w) >> (22 + (slot))) & 1u)          // first block of that chunk (accumulator reset)
+#define SW_DONE(w, slot) (((w) >> (24 + (slot))) & 1u)           // last block of that chunk (epilogue may drain)
+
 struct F8Maps {            // tensor maps of the three B planes (128-row and 32-row boxes) and of the K* cache
   CUtensorMap hi128, hi32, c1_128, c1_32, c2_128, c2_32, kc;
 };
@@ -94,7 +117,7 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
   constexpr int NSTA = 3, NSTB = 3;
   constexpr int NSL = F8_NSL;                   // train-slice ring (TMA bulk copies, one slice per fresh K-block)
   constexpr int GEN_WARPS = GW;
-  constexpr int CW = 256, NSLOT = 2, KSH = 2;
+  constexpr int CW = 256;
   constexpr int XT_STRIDE = (DP + 2) * FK;     // floats per slice: DP coordinate rows, sigma_f2 alpha, |b|^2
   constexpr uint32_t SLICE_BYTES = XT_STRIDE * 4;
   // D = f32, A = B = fp16 / e4m3 (format code 0 in both kinds), K-major, M = 256 (pair); N is patched per unit
@@ -102,33 +125,11 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = prm.gp.d, np = prm.gp.n_pad;
   const int nkb = np / FK;
-  const int n_chunks = (np + CW - 1) / CW;
-  const int n_pass = (n_chunks + NSLOT - 1) / NSLOT;
   const long long n_tiles = (prm.m + FM - 1) / FM;
   const long long n_iter = (n_tiles + gridDim.x - 1) / gridDim.x;   // both CTAs of a pair walk the same sequence
   const uint32_t crank = cluster_rank();
   const bool leader = crank == 0;
-  const bool use_cache = prm.kcache != nullptr;
-  auto last_kb = [&](int c) { return min(((c + 1) << KSH) - 1, nkb - 1); };
-  // K-blocks of pass p: [0, kb_cached) were generated by earlier passes and come back from the L2 cache,
-  // [kb_cached, kb_end) are generated now
-  auto pass_kb_end = [&](int p) { return last_kb(min(NSLOT * p + NSLOT - 1, n_chunks - 1)) + 1; };
-  auto pass_kb_cached = [&](int p) { return (use_cache && p > 0) ? pass_kb_end(p - 1) : 0; };
-  // Order in which a pass walks its K-blocks: fresh and cached blocks ALTERNATE (F0 C0 F1 C1 ...), so that the
-  // generators work on the next fresh block while the tensor core multiplies a reloaded one.  In block order
-  // (all cached blocks first) the generators idle through the reloads and the MMA then starves on the fresh run.
-  auto seq_kb = [&](int kb_cached, int kb_end, int i) {
-    const int nf = kb_end - kb_cached, nc = kb_cached, nmin = min(nf, nc);
-    if (i < 2 * nmin) return (i & 1) ? (i >> 1) : kb_cached + (i >> 1);
-    return nf > nc ? kb_cached + (i - nc) : (i - nf);
-  };
-  // position of the last K-block of chunk c in that order (the chunk's accumulator is complete after it)
-  auto last_pos = [&](int kb_cached, int kb_end, int c) {
-    const int lk = last_kb(c);
-    int i = kb_end - 1;
-    while (i > 0 && seq_kb(kb_cached, kb_end, i) > lk) --i;
-    return i;
-  };
+  const int n_steps = prm.n_steps;
   // columns of chunk c that K-block kb touches: [r0, r0 + ncols) of the chunk (rows of L^-1 above the diagonal band
   // and beyond n_pad are zero)
   auto unit_r0 = [&](int c, int kb) { return max(0, kb - 4 * c) * 64; };
@@ -147,9 +148,18 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
   uint64_t *xc_full = bars + 27, *xc_empty = bars + 29;
   uint32_t *tmem_slot = (uint32_t *)(bars + 32);
   double *inv_ell = (double *)(bars + 34);
+  uint32_t *store_seq = (uint32_t *)(bars + 50);               // [128] warp 3's private table (K* cache store order)
+  uint32_t *landed = store_seq + 128;                          // (spare words)
+  // the step schedule is staged in shared memory (every role reads a word per step, and with this much shared
+  // memory carved out there is next to no L1 left for a global table); very long schedules stay in global memory
+  uint32_t *sched_sm = landed + 4;
+  const uint32_t *sched = prm.sched_in_smem ? (const uint32_t *)sched_sm : prm.sched;
+  if (prm.sched_in_smem)
+    for (int i = tid; i < n_steps; i += blockDim.x) sched_sm[i] = __ldg(prm.sched + i);
 
   if (tid == 0) {
     for (int j = 0; j < DP; ++j) inv_ell[j] = j < d ? 1.0 / prm.gp.ell[j] : 0.0;
+    *landed = 0u;
     for (int s = 0; s < NSTA; ++s) {
       mbar_init(smem_u32(&a_full[s]), 2 * GEN_WARPS);
       mbar_init(smem_u32(&a_empty[s]), 2);                      // the MMA's commit + this CTA's cache thread
@@ -189,33 +199,32 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
       uint32_t st = 0, ph = 0;
       long long w_bempty = 0; const long long t_start = clock64();
       for (long long it = 0; it < n_iter; ++it) {
-        for (int p = 0; p < n_pass; ++p) {
-          const int c_first = NSLOT * p, c_last = min(c_first + NSLOT - 1, n_chunks - 1);
-          const int kb_end = pass_kb_end(p), kb_cached = pass_kb_cached(p);
-          for (int i = 0; i < kb_end; ++i) {
-            const int kb = seq_kb(kb_cached, kb_end, i);
-            for (int c = max(c_first, kb >> KSH); c <= c_last; ++c) {
-              const int ncols = unit_ncols(c, kb), rows = ncols >> 1;          // rows of the band this CTA holds
-              const int row0 = c * CW + unit_r0(c, kb) + (int)crank * rows;
-              mbar_wait_prof(smem_u32(&b_empty[st]), ph ^ 1, 64, w_bempty, pon);
-              F8_TRACE(0, kb * 8 + c);
-              const uint32_t dst = smem_u32(sB + st * STAGE_BYTES);
-              // the leader alone arms its barrier, with the bytes of BOTH halves (256 B per band row over the planes)
-              const uint32_t full = mapa_rank(smem_u32(&b_full[st]), 0);
-              if (leader) mbar_expect_tx(smem_u32(&b_full[st]), (uint32_t)(ncols * 256));
-              if (rows == 128) {
-                tma_load_2d_2sm(dst, &maps.hi128, full, kb * FK, row0);
-                tma_load_2d_2sm(dst + F8_OFF_C1, &maps.c1_128, full, kb * FK, row0);
-                tma_load_2d_2sm(dst + F8_OFF_C2, &maps.c2_128, full, kb * FK, row0);
-              } else {
-                for (int rr = 0; rr < rows; rr += 32) {
-                  tma_load_2d_2sm(dst + (uint32_t)(rr * 128), &maps.hi32, full, kb * FK, row0 + rr);
-                  tma_load_2d_2sm(dst + F8_OFF_C1 + (uint32_t)(rr * 64), &maps.c1_32, full, kb * FK, row0 + rr);
-                  tma_load_2d_2sm(dst + F8_OFF_C2 + (uint32_t)(rr * 64), &maps.c2_32, full, kb * FK, row0 + rr);
-                }
+        for (int si = 0; si < n_steps; ++si) {
+          const uint32_t w = sched[si];
+          const int kb = SW_KB(w);
+          for (int slot = 0; slot < 2; ++slot) {
+            const int c = SW_CHUNK(w, slot);
+            if (c < 0) continue;
+            const int ncols = unit_ncols(c, kb), rows = ncols >> 1;          // rows of the band this CTA holds
+            const int row0 = c * CW + unit_r0(c, kb) + (int)crank * rows;
+            mbar_wait_prof(smem_u32(&b_empty[st]), ph ^ 1, 64, w_bempty, pon);
+            F8_TRACE(0, kb * 8 + c);
+            const uint32_t dst = smem_u32(sB + st * STAGE_BYTES);
+            // the leader alone arms its barrier, with the bytes of BOTH halves (256 B per band row over the planes)
+            const uint32_t full = mapa_rank(smem_u32(&b_full[st]), 0);
+            if (leader) mbar_expect_tx(smem_u32(&b_full[st]), (uint32_t)(ncols * 256));
+            if (rows == 128) {
+              tma_load_2d_2sm(dst, &maps.hi128, full, kb * FK, row0);
+              tma_load_2d_2sm(dst + F8_OFF_C1, &maps.c1_128, full, kb * FK, row0);
+              tma_load_2d_2sm(dst + F8_OFF_C2, &maps.c2_128, full, kb * FK, row0);
+            } else {
+              for (int rr = 0; rr < rows; rr += 32) {
+                tma_load_2d_2sm(dst + (uint32_t)(rr * 128), &maps.hi32, full, kb * FK, row0 + rr);
+                tma_load_2d_2sm(dst + F8_OFF_C1 + (uint32_t)(rr * 64), &maps.c1_32, full, kb * FK, row0 + rr);
+                tma_load_2d_2sm(dst + F8_OFF_C2 + (uint32_t)(rr * 64), &maps.c2_32, full, kb * FK, row0 + rr);
               }
-              if (++st == NSTB) { st = 0; ph ^= 1; }
             }
+            if (++st == NSTB) { st = 0; ph ^= 1; }
           }
         }
       }
@@ -227,54 +236,50 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, tph = 0;
       long long w_afull = 0, w_bfull = 0, w_tempty = 0;
       for (long long it = 0; it < n_iter; ++it) {
-        for (int p = 0; p < n_pass; ++p) {
-          const int c_first = NSLOT * p, c_last = min(c_first + NSLOT - 1, n_chunks - 1);
-          const int kb_end = pass_kb_end(p), kb_cached = pass_kb_cached(p);
-          int lastp[NSLOT];
-          for (int c = c_first; c <= c_last; ++c) lastp[c - c_first] = last_pos(kb_cached, kb_end, c);
-          for (int i = 0; i < kb_end; ++i) {
-            const int kb = seq_kb(kb_cached, kb_end, i);
-            F8_TRACE(1, 0x80 | kb);
-            mbar_wait_prof(smem_u32(&a_full[sa]), pa, MMA_SLEEP_NS, w_afull, pon);
-            F8_TRACE(1, 0xC0 | kb);
-            tc_fence_after();
-            const uint32_t a_hi = smem_u32(sA + sa * STAGE_BYTES);
-            for (int c = max(c_first, kb >> KSH); c <= c_last; ++c) {
-              const int slot = c & (NSLOT - 1);
-              if (i == 0) {                                  // first touch of this accumulator slot (every chunk of the
-                                                             // pass takes part in the pass's first block)
-                mbar_wait_prof(smem_u32(&t_empty[slot]), ((tph >> slot) & 1) ^ 1, MMA_SLEEP_NS, w_tempty, pon);
-                tph ^= (1u << slot);
-                tc_fence_after();
-              }
-              const int r0 = unit_r0(c, kb), ncols = unit_ncols(c, kb);
-              const uint32_t dcol = tmem_base + (uint32_t)(slot * CW + r0);
-              const uint32_t idesc = IDESC | ((uint32_t)(ncols >> 3) << 17);
-              mbar_wait_prof(smem_u32(&b_full[sb]), pb, MMA_SLEEP_NS, w_bfull, pon);
-              F8_TRACE(1, kb * 4 + (c & 3));
+        for (int si = 0; si < n_steps; ++si) {
+          const uint32_t w = sched[si];
+          const int kb = SW_KB(w);
+          F8_TRACE(1, 0x80 | (kb & 31));
+          mbar_wait_prof(smem_u32(&a_full[sa]), pa, MMA_SLEEP_NS, w_afull, pon);
+          F8_TRACE(1, 0xC0 | (kb & 31));
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(sA + sa * STAGE_BYTES);
+          for (int slot = 0; slot < 2; ++slot) {
+            const int c = SW_CHUNK(w, slot);
+            if (c < 0) continue;
+            const uint32_t first = SW_FIRST(w, slot);
+            if (first) {                                   // the slot's previous chunk must have been drained
+              mbar_wait_prof(smem_u32(&t_empty[slot]), ((tph >> slot) & 1) ^ 1, MMA_SLEEP_NS, w_tempty, pon);
+              tph ^= (1u << slot);
               tc_fence_after();
-              const uint32_t b_hi = smem_u32(sB + sb * STAGE_BYTES);
-              if (!(prm.dbg & 1)) {
-#pragma unroll
-                for (int ks = 0; ks < FK / 16; ++ks)
-                  umma_bf16_2sm(dcol, make_sdesc(a_hi + ks * 32), make_sdesc(b_hi + ks * 32), idesc, (i > 0 || ks > 0) ? 1u : 0u);
-                if (!(prm.dbg & 4)) {
-#pragma unroll
-                  for (int ks = 0; ks < FK / 32; ++ks)
-                    umma_f8_2sm(dcol, make_sdesc64(a_hi + F8_OFF_C1 + ks * 32), make_sdesc64(b_hi + F8_OFF_C1 + ks * 32), idesc, 1u);
-#pragma unroll
-                  for (int ks = 0; ks < FK / 32; ++ks)
-                    umma_f8_2sm(dcol, make_sdesc64(a_hi + F8_OFF_C2 + ks * 32), make_sdesc64(b_hi + F8_OFF_C2 + ks * 32), idesc, 1u);
-                }
-              }
-              umma_commit_2sm(smem_u32(&b_empty[sb]));
-              if (i == lastp[c - c_first]) umma_commit_2sm(smem_u32(&t_full[slot]));      // chunk complete
-              if (++sb == NSTB) { sb = 0; pb ^= 1; }
             }
-            umma_commit_2sm(smem_u32(&a_empty[sa]));
-            F8_TRACE(1, 0x40 | kb);
-            if (++sa == NSTA) { sa = 0; pa ^= 1; }
+            const int r0 = unit_r0(c, kb), ncols = unit_ncols(c, kb);
+            const uint32_t dcol = tmem_base + (uint32_t)(slot * CW + r0);
+            const uint32_t idesc = IDESC | ((uint32_t)(ncols >> 3) << 17);
+            mbar_wait_prof(smem_u32(&b_full[sb]), pb, MMA_SLEEP_NS, w_bfull, pon);
+            F8_TRACE(1, (kb & 15) * 4 + (c & 3));
+            tc_fence_after();
+            const uint32_t b_hi = smem_u32(sB + sb * STAGE_BYTES);
+            if (!(prm.dbg & 1)) {
+#pragma unroll
+              for (int ks = 0; ks < FK / 16; ++ks)
+                umma_bf16_2sm(dcol, make_sdesc(a_hi + ks * 32), make_sdesc(b_hi + ks * 32), idesc, (!first || ks > 0) ? 1u : 0u);
+              if (!(prm.dbg & 4)) {
+#pragma unroll
+                for (int ks = 0; ks < FK / 32; ++ks)
+                  umma_f8_2sm(dcol, make_sdesc64(a_hi + F8_OFF_C1 + ks * 32), make_sdesc64(b_hi + F8_OFF_C1 + ks * 32), idesc, 1u);
+#pragma unroll
+                for (int ks = 0; ks < FK / 32; ++ks)
+                  umma_f8_2sm(dcol, make_sdesc64(a_hi + F8_OFF_C2 + ks * 32), make_sdesc64(b_hi + F8_OFF_C2 + ks * 32), idesc, 1u);
+              }
+            }
+            umma_commit_2sm(smem_u32(&b_empty[sb]));
+            if (SW_DONE(w, slot)) umma_commit_2sm(smem_u32(&t_full[slot]));      // chunk complete
+            if (++sb == NSTB) { sb = 0; pb ^= 1; }
           }
+          umma_commit_2sm(smem_u32(&a_empty[sa]));
+          F8_TRACE(1, 0x40 | (kb & 31));
+          if (++sa == NSTA) { sa = 0; pa ^= 1; }
         }
       }
       if (pon) { prm.prof[blockIdx.x * 16 + 2] = w_afull; prm.prof[blockIdx.x * 16 + 3] = w_bfull; prm.prof[blockIdx.x * 16 + 4] = w_tempty; }
@@ -304,24 +309,22 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
     // =============================== train slices + K* cache (one thread) =================
     // (a) keeps the ring of train slices NSL - 1 fresh blocks ahead of the generators: DP + 2 bulk copies of 256 B
     //     (coordinate rows, sigma_f2 alpha, |b|^2 of K-block kb) completing on s_full;
-    // (b) walks the A stages in block order: a FRESH block is copied to the per-CTA cache in L2 once every local
-    //     generator warp has written it (a_written), a CACHED block is streamed back into the stage (2-SM load, bytes
-    //     counted on the leader's a_full together with this CTA's share of the arrivals).  Either way the thread
-    //     then arrives on a_empty: a stage is free once the MMA has consumed it AND the cache copy has read it.
+    // (b) walks the A stages in step order: a FRESH block that a later chunk needs is copied to the per-CTA cache in
+    //     L2 once every local generator warp has written it (a_written), a CACHED block is streamed back into the
+    //     stage (2-SM load, bytes counted on the leader's a_full together with this CTA's share of the arrivals).
+    //     Either way the thread then arrives on a_empty: a stage is free once the MMA has consumed it AND the cache
+    //     copy has read it.  (Measured alternatives, all slower: reloads issued by the B producer -- blocking or
+    //     polling both cursors --, or by a generator thread when it passes the step.)
     if (elect_one()) {
-      long long it_s = 0; int p_s = 0, i_s = 0;
+      long long it_s = 0; int i_s = 0;
       bool s_done = n_iter == 0;
       uint32_t sl = 0, slph = 0;
       auto slice_next = [&]() {
         while (!s_done) {
-          const int kb_end = pass_kb_end(p_s), kb_cached = pass_kb_cached(p_s);
-          if (i_s >= kb_end) {
-            i_s = 0;
-            if (++p_s == n_pass) { p_s = 0; if (++it_s == n_iter) s_done = true; }
-            continue;
-          }
-          const int kb = seq_kb(kb_cached, kb_end, i_s++);
-          if (kb < kb_cached) continue;
+          if (i_s >= n_steps) { i_s = 0; if (++it_s == n_iter) s_done = true; continue; }
+          const uint32_t w = sched[i_s++];
+          if (!SW_FRESH(w)) continue;
+          const int kb = SW_KB(w);
           mbar_wait_sleep(smem_u32(&s_empty[sl]), slph ^ 1, 32);
           const uint32_t full = smem_u32(&s_full[sl]);
           mbar_expect_tx(full, SLICE_BYTES);
@@ -339,35 +342,40 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
       uint32_t wph = 0;                          // a_written completes a phase on FRESH uses of a stage only
       const uint32_t a_full_leader0 = mapa_rank(smem_u32(&a_full[0]), 0);
       unsigned char *kc = prm.kcache + (size_t)blockIdx.x * nkb * STAGE_BYTES;
+      // bulk stores of one thread complete in order: a reload of block kb waits until at most `younger` of them
+      // are pending, younger = copies issued after the one of kb (store_seq, this thread's private table)
+      uint32_t n_stores = 0;
       for (long long it = 0; it < n_iter; ++it) {
-        for (int p = 0; p < n_pass; ++p) {
-          const int kb_end = pass_kb_end(p), kb_cached = pass_kb_cached(p);
-          const bool store_cache = use_cache && (p + 1 < n_pass);
-          if (kb_cached > 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");   // earlier passes' stores landed
-          for (int i = 0; i < kb_end; ++i) {
-            const int kb = seq_kb(kb_cached, kb_end, i);
-            const uint32_t stage = smem_u32(sA + sa * STAGE_BYTES);
-            if (kb >= kb_cached) {
-              slice_next();
-              mbar_wait_sleep(smem_u32(&a_written[sa]), (wph >> sa) & 1, 64);
-              F8_TRACE(3, kb);
-              wph ^= 1u << sa;
-              if (store_cache) {
-                bulk_store(kc + (size_t)kb * STAGE_BYTES, stage, STAGE_BYTES);
-                asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-              }
-            } else {
-              const uint32_t full_leader = a_full_leader0 + (uint32_t)(sa * 8);
-              mbar_wait_sleep(smem_u32(&a_empty[sa]), pa ^ 1, 32);
-              F8_TRACE(3, 0x40 | kb);
-              mbar_expect_tx_remote(full_leader, STAGE_BYTES);
-              mbar_arrive_n_remote(full_leader, GEN_WARPS - 1);
-              tma_load_2d_2sm(stage, &maps.kc, full_leader, 0, (int)((blockIdx.x * nkb + kb) * 256));
+        for (int si = 0; si < n_steps; ++si) {
+          const uint32_t w = sched[si];
+          const int kb = SW_KB(w);
+          const uint32_t stage = smem_u32(sA + sa * STAGE_BYTES);
+          if (SW_FRESH(w)) {
+            slice_next();
+            mbar_wait_sleep(smem_u32(&a_written[sa]), (wph >> sa) & 1, 64);
+            F8_TRACE(3, kb);
+            wph ^= 1u << sa;
+            if (SW_STORE(w)) {
+              bulk_store(kc + (size_t)kb * STAGE_BYTES, stage, STAGE_BYTES);
+              store_seq[kb] = n_stores++;
+              asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
             }
-            mbar_arrive(smem_u32(&a_empty[sa]));
-            F8_TRACE(3, 0x80 | kb);
-            if (++sa == NSTA) { sa = 0; pa ^= 1; }
+          } else {
+            const uint32_t younger = n_stores - 1u - store_seq[kb];
+            if (younger == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+            else if (younger == 1) asm volatile("cp.async.bulk.wait_group 1;\n" ::: "memory");
+            else if (younger == 2) asm volatile("cp.async.bulk.wait_group 2;\n" ::: "memory");
+            else if (younger == 3) asm volatile("cp.async.bulk.wait_group 3;\n" ::: "memory");
+            const uint32_t full_leader = a_full_leader0 + (uint32_t)(sa * 8);
+            mbar_wait_sleep(smem_u32(&a_empty[sa]), pa ^ 1, 32);
+            F8_TRACE(3, 0x40 | kb);
+            mbar_expect_tx_remote(full_leader, STAGE_BYTES);
+            mbar_arrive_n_remote(full_leader, GEN_WARPS - 1);
+            tma_load_2d_2sm(stage, &maps.kc, full_leader, 0, (int)((blockIdx.x * nkb + kb) * 256));
           }
+          mbar_arrive(smem_u32(&a_empty[sa]));
+          F8_TRACE(3, 0x80 | kb);
+          if (++sa == NSTA) { sa = 0; pa ^= 1; }
         }
       }
       asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
@@ -383,27 +391,31 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
     for (long long it = 0; it < n_iter; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
       double ss = 0.0;
-      for (int c = 0; c < n_chunks; ++c) {
-        const int slot = c & (NSLOT - 1);
-        mbar_wait_sleep(smem_u32(&t_full[slot]), (fph >> slot) & 1, 200);
-        F8_TRACE_E(c);
-        fph ^= (1u << slot);
-        tc_fence_after();
-        float part[4] = {0.f, 0.f, 0.f, 0.f};
-        const int ncw = min(CW, np - c * CW);
+      for (int si = 0; si < n_steps; ++si) {
+        const uint32_t w = sched[si];
+        for (int slot = 0; slot < 2; ++slot) {
+          if (!SW_DONE(w, slot)) continue;
+          const int c = SW_CHUNK(w, slot);
+          mbar_wait_sleep(smem_u32(&t_full[slot]), (fph >> slot) & 1, 200);
+          F8_TRACE_E(c);
+          fph ^= (1u << slot);
+          tc_fence_after();
+          float part[4] = {0.f, 0.f, 0.f, 0.f};
+          const int ncw = min(CW, np - c * CW);
 #pragma unroll 1
-        for (int q = 0; q < ncw / 32; ++q) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * CW + q * 32), v);
-          tmem_ld_wait();
+          for (int q = 0; q < ncw / 32; ++q) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(slot * CW + q * 32), v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) { float f = __uint_as_float(v[e]); part[e & 3] = fmaf(f, f, part[e & 3]); }
+            for (int e = 0; e < 32; ++e) { float f = __uint_as_float(v[e]); part[e & 3] = fmaf(f, f, part[e & 3]); }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(t_empty_leader + (uint32_t)(slot * 8));
+          F8_TRACE_E(0x40 | c);
+          ss += (double)((part[0] + part[1]) + (part[2] + part[3]));
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_remote(t_empty_leader + (uint32_t)(slot * 8));
-        F8_TRACE_E(0x40 | c);
-        ss += (double)((part[0] + part[1]) + (part[2] + part[3]));
       }
       const long long cg = tile * FM + row;
       if (cg < prm.m) {
@@ -467,13 +479,13 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&xc_empty[b]));                   // xc[b] may be refilled
-      for (int p = 0; p < n_pass; ++p) {
-        const int kb_end = pass_kb_end(p), kb_cached = pass_kb_cached(p);
-        for (int i = 0; i < kb_end; ++i) {
-          const int kb = seq_kb(kb_cached, kb_end, i);
-          if (kb < kb_cached) {
-            // a K* block of an earlier pass (reloaded by warp 3).  Every generator warp still waits for the stage's
-            // release: a warp that skipped ahead through a run of cached blocks would get more than one barrier
+      {
+        for (int si = 0; si < n_steps; ++si) {
+          const uint32_t w = sched[si];
+          const int kb = SW_KB(w);
+          if (!SW_FRESH(w)) {
+            // a K* block streamed back from the cache (by warp 3).  Every generator warp still waits for the stage's
+            // release: a warp that skipped ahead through a run of reloads would get more than one barrier
             // phase ahead of the MMA, and a parity wait cannot tell phases two apart.
             mbar_wait_sleep(a_empty_u + sa * 8, pa ^ 1, 128);
             if (++sa == NSTA) { sa = 0; pa ^= 1; }
@@ -608,6 +620,131 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
 }
 
 // ---- host side ------------------------------------------------------------------------------
+// Step schedule of one tile (see the header).  max_run <= 0: the PASS schedule (default, below).  max_run >= 1: the
+// ROLLING schedule (OMBO_F8_MAXRUN, experimental).  The generators deliver block f = 0 .. nkb-1 in order, one per `tg`
+// units of MMA time (unit = one 256-column chunk x one 64-deep K-block x the three products).  Two TMEM slots; a
+// chunk opens in the slot that frees, with the already generated blocks it needs queued as reloads.  Reloads are
+// issued (a) when a chunk needs no further fresh block and only its queue keeps its slot busy, (b) in the MMA time
+// a fresh step leaves over (tg - its units, at most one unit banked; never more than max_run in a row), (c) at the end.  A reload that both open
+// chunks still need serves both (one stage fill, two units).
+void f8_build_schedule(int np, double tg, int max_run, std::vector<unsigned int> &steps) {
+  const int nkb = np / FK, n_chunks = (np + 255) / 256;
+  auto last_kb = [&](int c) { return std::min(4 * c + 3, nkb - 1); };
+  if (max_run <= 0) {
+    // PASS schedule (the default, measured faster on the three-stage A ring -- DESIGN.md section 4): chunks 2p and
+    // 2p+1 share pass p; the blocks earlier passes generated come back as reloads that serve BOTH chunks (two units
+    // per stage fill) and alternate with the pass's fresh blocks (F C F C ...), so that the generators work on the
+    // next fresh block while the tensor core multiplies a reloaded one.
+    steps.clear();
+    for (int c0 = 0, cached = 0; c0 < n_chunks; c0 += 2) {
+      const int c1 = c0 + 1 < n_chunks ? c0 + 1 : -1;
+      const int end = last_kb(c1 >= 0 ? c1 : c0) + 1, nf = end - cached, nc = cached, nmin = std::min(nf, nc);
+      const size_t first = steps.size();
+      for (int i = 0; i < end; ++i) {
+        int kb;
+        if (i < 2 * nmin) kb = (i & 1) ? (i >> 1) : cached + (i >> 1);
+        else kb = nf > nc ? cached + (i - nc) : (i - nf);
+        unsigned int w = (unsigned int)kb | (kb >= cached ? 1u << 8 : 0u);
+        if (kb <= last_kb(c0)) w |= (unsigned int)(c0 + 1) << 10;
+        if (c1 >= 0) w |= (unsigned int)(c1 + 1) << 16;
+        steps.push_back(w);
+      }
+      // FIRST on each chunk's first step of the pass, DONE on its last
+      for (int s = 0; s < 2; ++s) {
+        long fi = -1, la = -1;
+        for (size_t i = first; i < steps.size(); ++i)
+          if ((steps[i] >> (10 + 6 * s)) & 63u) { if (fi < 0) fi = (long)i; la = (long)i; }
+        if (fi >= 0) { steps[fi] |= 1u << (22 + s); steps[la] |= 1u << (24 + s); }
+      }
+      cached = end;
+    }
+    std::vector<char> reloaded(nkb, 0);
+    for (unsigned int w : steps) if (!((w >> 8) & 1u)) reloaded[w & 0xFFu] = 1;
+    for (unsigned int &w : steps) if (((w >> 8) & 1u) && reloaded[w & 0xFFu]) w |= 1u << 9;
+    return;
+  }
+  auto units = [&](int c, int kb) {
+    const int r0 = std::max(0, kb - 4 * c) * 64;
+    return (std::min(256, np - c * 256) - r0) / 256.0;
+  };
+  int slot_c[2] = {-1, -1};
+  bool started[2] = {false, false};
+  std::deque<int> pend[2];
+  int next_c = 0, gen = -1;
+  steps.clear();
+  auto open_slot = [&](int s) {
+    pend[s].clear();
+    started[s] = false;
+    if (next_c >= n_chunks) { slot_c[s] = -1; return; }
+    const int c = next_c++;
+    slot_c[s] = c;
+    for (int k = 0; k <= std::min(gen, last_kb(c)); ++k) pend[s].push_back(k);
+  };
+  auto done = [&](int s) { return slot_c[s] >= 0 && pend[s].empty() && gen >= last_kb(slot_c[s]); };
+  auto any_pend = [&]() { return (slot_c[0] >= 0 && !pend[0].empty()) || (slot_c[1] >= 0 && !pend[1].empty()); };
+  auto add_chunk = [&](unsigned int &w, int s, int kb, double &u, bool (&fin)[2]) {
+    w |= (unsigned int)(slot_c[s] + 1) << (10 + 6 * s);
+    if (!started[s]) { w |= 1u << (22 + s); started[s] = true; }
+    u += units(slot_c[s], kb);
+    if (done(s)) { w |= 1u << (24 + s); fin[s] = true; }
+  };
+  auto emit_cached = [&]() {
+    int sp = -1;
+    for (int s = 0; s < 2; ++s)
+      if (slot_c[s] >= 0 && !pend[s].empty() && (sp < 0 || slot_c[s] < slot_c[sp])) sp = s;
+    const int kb = pend[sp].front();
+    unsigned int w = (unsigned int)kb;
+    double u = 0.0;
+    bool fin[2] = {false, false};
+    for (int s = 0; s < 2; ++s)
+      if (slot_c[s] >= 0 && !pend[s].empty() && pend[s].front() == kb) {
+        pend[s].pop_front();
+        add_chunk(w, s, kb, u, fin);
+      }
+    steps.push_back(w);
+    for (int s = 0; s < 2; ++s) if (fin[s]) open_slot(s);
+    return u;
+  };
+  open_slot(0);
+  open_slot(1);
+  double carry = 0.0;
+  for (int f = 0; f < nkb; ++f) {
+    // a chunk that needs no further fresh block holds its slot only for its reloads: finish them first
+    for (;;) {
+      bool stuck = false;
+      for (int s = 0; s < 2; ++s) stuck |= slot_c[s] >= 0 && last_kb(slot_c[s]) < f && !pend[s].empty();
+      if (!stuck) break;
+      carry -= emit_cached();
+    }
+    gen = f;
+    unsigned int w = (unsigned int)f | (1u << 8);
+    double u = 0.0;
+    bool fin[2] = {false, false};
+    for (int s = 0; s < 2; ++s)
+      if (slot_c[s] >= 0 && f <= last_kb(slot_c[s])) add_chunk(w, s, f, u, fin);
+    steps.push_back(w);
+    for (int s = 0; s < 2; ++s) if (fin[s]) open_slot(s);
+    // at most max_run reloads in a row: the A ring is three stages deep, and a longer run of reloads would hold
+    // the stage the generators need for the second half of their next block
+    double budget = carry + tg - u;
+    for (int run = 0; run < max_run && budget > 0.0 && any_pend(); ++run) budget -= emit_cached();
+    carry = std::min(budget, 1.0);
+  }
+  while (any_pend()) emit_cached();
+  // fresh blocks that some later step reloads have to be copied to the cache
+  std::vector<char> reloaded(nkb, 0);
+  for (unsigned int w : steps) if (!((w >> 8) & 1u)) reloaded[w & 0xFFu] = 1;
+  for (unsigned int &w : steps) if (((w >> 8) & 1u) && reloaded[w & 0xFFu]) w |= 1u << 9;
+}
+
+// debug / test hook (not part of the public header): the schedule for n_pad as the kernel will walk it
+extern "C" int ombo_debug_f8_schedule(int n_pad, double tg, int max_run, unsigned int *out, int cap) {
+  std::vector<unsigned int> steps;
+  f8_build_schedule(n_pad, tg, max_run, steps);
+  for (int i = 0; i < (int)steps.size() && i < cap; ++i) out[i] = steps[i];
+  return (int)steps.size();
+}
+
 static int make_plane_map(CUtensorMap *map, const void *base, int n_pad, int esz, int box_rows) {
   PFN_encodeTiled_t enc = ombo_get_encode_tiled();
   if (!enc) { ombo_set_error("cuTensorMapEncodeTiled is not available from the driver"); return OMBO_ERR_CUDA; }
@@ -624,9 +761,11 @@ static int make_plane_map(CUtensorMap *map, const void *base, int n_pad, int esz
 }
 
 template <int DP, int R, int GW>
-static int launch_fast8(ombo_ctx *ctx, const F8Maps &maps, const FastParams &prm, int grid, cudaStream_t s) {
-  const size_t smem = (size_t)6 * STAGE_BYTES + 2 * (size_t)DP * FM * 4 + (size_t)F8_NSL * (DP + 2) * FK * 4 +
-                      8 * FM * 4 + 16 + 34 * 8 + 16 * 8 + 1024;
+static int launch_fast8(ombo_ctx *ctx, const F8Maps &maps, FastParams prm, int grid, cudaStream_t s) {
+  size_t smem = (size_t)6 * STAGE_BYTES + 2 * (size_t)DP * FM * 4 + (size_t)F8_NSL * (DP + 2) * FK * 4 +
+                      8 * FM * 4 + 16 + 34 * 8 + 16 * 8 + 128 * 4 + 16 + 1024;
+  prm.sched_in_smem = smem + (size_t)prm.n_steps * 4 <= 227 * 1024 ? 1 : 0;
+  if (prm.sched_in_smem) smem += (size_t)prm.n_steps * 4;
   // per device, not per process: the attribute belongs to the (function, device) pair
   OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast8<DP, R, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(ctx, s);
@@ -675,7 +814,23 @@ int ombo_posterior_fast8(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lo
   int grid = (int)(tiles < ctx->num_sms ? tiles : ctx->num_sms);
   grid = (grid + 1) / 2 * 2;                    // whole pairs; a surplus CTA runs a dummy tile
   if (grid > ctx->num_sms) grid = ctx->num_sms / 2 * 2;
-  if (gp.n_pad > 512) {                          // more than one TMEM pass: K* blocks are cached in L2 between passes
+  if (ctx->f8_sched_np != gp.n_pad) {              // step schedule of a tile: a function of n_pad (and the knob) only
+    std::vector<unsigned int> steps;
+    f8_build_schedule(gp.n_pad, ctx->knobs.f8_tg, ctx->knobs.f8_max_run, steps);
+    if ((int)steps.size() > ctx->f8_sched_cap) {
+      if (ctx->f8_sched) OMBO_CUDA(cudaFree(ctx->f8_sched));
+      ctx->f8_sched = nullptr;
+      OMBO_CUDA(cudaMalloc(&ctx->f8_sched, steps.size() * sizeof(unsigned int)));
+      ctx->f8_sched_cap = (int)steps.size();
+    }
+    OMBO_CUDA(cudaStreamSynchronize(s));            // a launch in flight may still read the old table
+    OMBO_CUDA(cudaMemcpy(ctx->f8_sched, steps.data(), steps.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
+    ctx->f8_sched_np = gp.n_pad;
+    ctx->f8_sched_len = (int)steps.size();
+  }
+  prm.sched = ctx->f8_sched;
+  prm.n_steps = ctx->f8_sched_len;
+  if (gp.n_pad > 512) {                          // more than two chunks: generated K* blocks are cached in L2 for later chunks
     rc = ombo_ws_reserve(&ctx->ws_scratch, &ctx->ws_scratch_bytes, (size_t)grid * (gp.n_pad / FK) * STAGE_BYTES);
     if (rc) return rc;
     prm.kcache = (unsigned char *)ctx->ws_scratch;
