@@ -15,19 +15,10 @@
 // warp shuffle -> block (smem) -> per-block partial -> one final block; ties resolve to the
 // lowest global index (np.argmax), NaN is treated as -inf.
 #include "common.cuh"
+#include "acq_math.cuh"
 
 #define ACQ_THREADS 256
 
-__device__ __forceinline__ double Phi(double t) { return 0.5 * erfc(-t * 0.70710678118654752440); }
-__device__ __forceinline__ double phi(double t) { return exp(-(t * t) / 2.0) / 2.50662827463100050242; }
-// FP32 twins for the fast precision mode (tolerance 1e-3): erfcf keeps its relative accuracy in the tails,
-// exp goes through MUFU.EX2 -- the FP64 pipe of the B200 is ~60x narrower than the FP32 one
-__device__ __forceinline__ float Phi(float t) { return 0.5f * erfcf(-t * 0.70710678f); }
-__device__ __forceinline__ float phi(float t) { return __expf(-0.5f * t * t) * 0.39894228f; }
-__device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
-__device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
-__device__ __forceinline__ float fmax_t(float a, float b) { return fmaxf(a, b); }
-__device__ __forceinline__ double fmax_t(double a, double b) { return fmax(a, b); }
 
 // ---- scalarisations (scalarisations.py) --------------------------------------------------
 __device__ double scalarise(const ombo_acq &a, const double *F) {
@@ -123,20 +114,6 @@ __device__ __forceinline__ T ei_value(T mu, T var, T best, T eps) {
   return s * (g * Phi(g) + phi(g));
 }
 
-// ---- arg-max helpers ---------------------------------------------------------------------
-struct BestPair { double v; long long i; };
-__device__ __forceinline__ bool better(double v, long long i, double bv, long long bi) {
-  return (v > bv) || (v == bv && i < bi);
-}
-__device__ __forceinline__ BestPair warp_best(BestPair b) {
-  for (int o = 16; o; o >>= 1) {
-    double ov = __shfl_xor_sync(0xffffffffu, b.v, o);
-    long long oi = __shfl_xor_sync(0xffffffffu, b.i, o);
-    if (better(ov, oi, b.v, b.i)) { b.v = ov; b.i = oi; }
-  }
-  return b;
-}
-
 extern __shared__ __align__(16) double acq_smem[];
 
 // T = double: the reference's arithmetic (FP64 precision mode, all goldens).  T = float: the fast precision mode
@@ -166,33 +143,8 @@ k_acquire(ombo_acq a, int n_gp, const double *__restrict__ mu, const double *__r
     switch (a.kind) {
       case OMBO_ACQ_EHVI2D: {
         const int P = a.n_pf;
-        const T *y1 = cst, *y2 = cst + (P + 2);
-        const bool exact = (a.semantics == OMBO_SEM_EXACT);
-        // reference: 'sigma' = flattened sample covariance (util_functions.py:163,167,:115)
-        const T s0 = exact ? sqrt_t(vars[0]) : vars[0] * (T)a.cache_c00;
-        const T s1 = exact ? sqrt_t(vars[1]) : vars[0] * (T)a.cache_c01;
-        const T m0 = mus[0], m1 = mus[1];
-        T sum1 = 0, sum2 = 0;
-        T tp = (y1[0] - m0) / s0;
-        T cdf_p = Phi(tp), pdf_p = phi(tp);
-        for (int i = 1; i <= P; ++i) {
-          T t = (y1[i] - m0) / s0;
-          T cdf_t = Phi(t), pdf_t = phi(t);
-          T t2 = (y2[i] - m1) / s1;
-          T psi2 = s1 * phi(t2) + (y2[i] - m1) * Phi(t2);
-          sum1 = sum1 + (y1[i - 1] - y1[i]) * cdf_t * psi2;
-          T psi_a = s0 * pdf_p + (y1[i - 1] - m0) * cdf_p;
-          T psi_b = s0 * pdf_t + (y1[i - 1] - m0) * cdf_t;
-          sum2 = sum2 + (psi_a - psi_b) * psi2;
-          cdf_p = cdf_t; pdf_p = pdf_t;
-        }
-        if (exact) {   // the (P+1)-th stripe the reference drops; y1[P+1] = -inf taken as a limit
-          T t2 = (y2[P + 1] - m1) / s1;
-          T psi2 = s1 * phi(t2) + (y2[P + 1] - m1) * Phi(t2);
-          T psi_a = s0 * pdf_p + (y1[P] - m0) * cdf_p;
-          sum2 = sum2 + psi_a * psi2;
-        }
-        r = sum1 + sum2;
+        r = ehvi2d_value<T>(mus[0], mus[1], vars[0], vars[1], cst, cst + (P + 2), P, a.semantics == OMBO_SEM_EXACT,
+                            (T)a.cache_c00, (T)a.cache_c01);
       } break;
       case OMBO_ACQ_EHVI3D:
       case OMBO_ACQ_EXPECTED_DECOMP: {
@@ -340,6 +292,13 @@ int ombo_pack_key_impl(ombo_ctx *ctx, const ombo_best *best_dev, long long *key_
 
 int ombo_best_init(ombo_ctx *ctx, ombo_best *best_dev, cudaStream_t s) {
   k_best_init<<<1, 1, 0, s>>>(best_dev);
+  ctx->launches += 1;
+  OMBO_CUDA(cudaGetLastError());
+  return OMBO_OK;
+}
+
+int ombo_argmax_merge(ombo_ctx *ctx, int n_partials, ombo_best *best_dev, cudaStream_t s) {
+  k_argmax_final<<<1, 1024, 0, s>>>((const ombo_best *)ctx->ws_partial, n_partials, best_dev);
   ctx->launches += 1;
   OMBO_CUDA(cudaGetLastError());
   return OMBO_OK;

@@ -68,9 +68,13 @@ int ombo_ctx_create(int device, ombo_ctx **out) {
     k.fast_gen_warps = geti("OMBO_FAST_GEN_WARPS", 8);
     k.f8_max_run = geti("OMBO_F8_MAXRUN", 0);
     { const char *e = getenv("OMBO_F8_TG"); k.f8_tg = e ? atof(e) : 3.0; }
+    k.chunk_log2 = geti("OMBO_CHUNK_LOG2", OMBO_CHUNK_DEV_LOG2);
+    if (k.chunk_log2 < 10) k.chunk_log2 = 10;
+    if (k.chunk_log2 > 26) k.chunk_log2 = 26;
     k.no_f8c = getenv("OMBO_NO_F8C") != nullptr;
     { const char *e = getenv("OMBO_F8C_KAPPA"); k.f8c_kappa = e ? atof(e) : OMBO_F8C_KAPPA_DEFAULT; }
     k.acq_fp64 = getenv("OMBO_ACQ_FP64") != nullptr;
+    k.no_fuse = getenv("OMBO_NO_FUSE") != nullptr;
   }
   OMBO_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
@@ -222,6 +226,7 @@ static int score_pass(ombo_ctx *ctx, const ombo_gp *gps, int n_gp, const ombo_po
     var = mu + (size_t)n_gp * count;
     ld = count;
   }
+  int fused = 0;
   for (int g = 0; g < n_gp; ++g) {
     GpDev gd = gp_dev_view(gps[g]);
     // K2 is skipped for GPs whose variance nothing reads (the caller did not ask for the posterior and
@@ -240,11 +245,28 @@ static int score_pass(ombo_ctx *ctx, const ombo_gp *gps, int n_gp, const ombo_po
         default: want_var = true;
       }
     }
+    // K4 + K5 fused behind the last model's K2 (fast mode, 2-D EHVI, nobody asked for the posterior itself): the
+    // f8c kernel's epilogue warps evaluate the EHVI from registers and keep a per-CTA arg-max, so this model's
+    // mu / var are never written and k_acquire does not run (ehvi2d_value is the same function either way)
+    FuseAcq fq;
+    const bool try_fuse = precision == OMBO_PREC_FAST && g == n_gp - 1 && n_gp == 2 && acq->kind == OMBO_ACQ_EHVI2D &&
+                          want_var && !out_mu && !out_var && !ctx->knobs.no_fuse && !ctx->knobs.acq_fp64 &&
+                          (out_acq || best_dev);
+    if (try_fuse) {
+      memset(&fq, 0, sizeof(fq));
+      fq.n_pf = acq->n_pf; fq.exact = acq->semantics == OMBO_SEM_EXACT;
+      fq.c00 = (float)acq->cache_c00; fq.c01 = (float)acq->cache_c01;
+      fq.mu0 = mu; fq.var0 = var; fq.stripes = acq->stripes;
+      fq.out_acq = out_acq ? out_acq + first : nullptr;
+      fq.index_base = pd.index_base;
+    }
     int rc = (precision == OMBO_PREC_FP64)
                  ? ombo_posterior_fp64(ctx, gd, pd, count, mu + (size_t)g * ld, var + (size_t)g * ld, want_var, s)
-                 : ombo_posterior_fast(ctx, gd, pd, count, mu + (size_t)g * ld, var + (size_t)g * ld, want_var, s);
+                 : ombo_posterior_fast(ctx, gd, pd, count, mu + (size_t)g * ld, var + (size_t)g * ld, want_var, s,
+                                       try_fuse ? &fq : nullptr, &fused);
     if (rc) return rc;
   }
+  if (fused) return best_dev ? ombo_argmax_merge(ctx, fused, best_dev, s) : OMBO_OK;
   if (acq->kind != OMBO_ACQ_NONE)
     return ombo_acquire(ctx, acq, n_gp, mu, var, count, ld, pd.index_base, out_acq ? out_acq + first : nullptr,
                         best_dev, s, precision == OMBO_PREC_FAST);
@@ -261,8 +283,9 @@ int ombo_score(ombo_ctx *ctx, const ombo_gp *gps, int n_gp, const ombo_pool *poo
   cudaStream_t s = (cudaStream_t)stream;
   if (best_dev) { rc = ombo_best_init(ctx, best_dev, s); if (rc) return rc; }
   const size_t esz = pool->dtype == 0 ? 8 : 4;
-  for (long long first = 0; first < pool->m; first += OMBO_CHUNK) {
-    long long count = pool->m - first < OMBO_CHUNK ? pool->m - first : OMBO_CHUNK;
+  const long long chunk = 1LL << ctx->knobs.chunk_log2;
+  for (long long first = 0; first < pool->m; first += chunk) {
+    long long count = pool->m - first < chunk ? pool->m - first : chunk;
     const void *X = pool->X ? (const char *)pool->X + (size_t)first * pool->d * esz : nullptr;
     rc = score_pass(ctx, gps, n_gp, pool, X, first, count, acq, precision, out_mu, out_var, out_acq, pool->m,
                     best_dev, s);

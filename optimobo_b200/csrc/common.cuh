@@ -14,7 +14,11 @@
 #define OMBO_PAD 128          // n_pad granularity (GEMM N-chunk)
 #define OMBO_PROF_MAX 4096
 #define OMBO_F8C_KAPPA_DEFAULT 100.0   // conditioning limit of the f8c operand format (measured)
-#define OMBO_CHUNK (1 << 20)  // candidates scored per pass through the posterior workspace
+#define OMBO_CHUNK (1 << 20)  // candidates per pass of the HOST entry (H2D staging granularity: copy i+1 overlaps pass i)
+// device pools: candidates per pass through the posterior workspace (OMBO_CHUNK_LOG2).  A launch of the persistent
+// posterior kernels loses about one tile time to fill / drain and up to one tile per CTA to the ragged last wave:
+// 2^22 instead of 2^20 candidates per launch takes that from ~3 % to under 1 % of the kernel time at C5.
+#define OMBO_CHUNK_DEV_LOG2 22
 
 void ombo_set_error(const char *fmt, ...);
 
@@ -46,9 +50,11 @@ struct ombo_knobs {
   int fast_gen_warps;     // OMBO_FAST_GEN_WARPS: 8 (default) or 16 K1 generator warps in the f8c kernel
   int f8_max_run;         // OMBO_F8_MAXRUN: most reload steps in a row between two generated blocks
   double f8_tg;           // OMBO_F8_TG: generator time per K-block in units of one 256-column MMA unit (schedule)
+  int chunk_log2;         // OMBO_CHUNK_LOG2: device-pool candidates per pass = 2^chunk_log2
   int no_f8c;             // OMBO_NO_F8C: never choose the fp16 + 2 x e4m3 operand format
   double f8c_kappa;       // OMBO_F8C_KAPPA: conditioning limit of that format
   int acq_fp64;           // OMBO_ACQ_FP64: keep the FP64 acquisition kernel in fast mode
+  int no_fuse;            // OMBO_NO_FUSE: never fuse the 2-D EHVI + arg-max into the f8c kernel's epilogue
 };
 
 struct ombo_ctx {
@@ -166,15 +172,35 @@ struct PoolDev {
   double lo[OMBO_MAX_DIM], span[OMBO_MAX_DIM];
 };
 
+// f8c kernel: 2-D EHVI and the per-CTA arg-max evaluated by the epilogue warps of the LAST model's launch (K4 + K5
+// fused behind K2: the model's mu / var never leave the SM, the other model's come from the posterior workspace)
+struct FuseAcq {
+  int on;                      // 0: plain posterior launch (mu_out / var_out written)
+  int n_pf, exact;             // stripes y1[0..P+1], y2[0..P+1]; semantics flag of ehvi2d_value
+  float c00, c01;              // reference semantics: flattened sample covariance entries
+  const double *mu0, *var0;    // posterior of model 0 for the same candidates
+  const double *stripes;       // device, 2 (P + 2) doubles
+  double *out_acq;             // optional per-candidate values
+  ombo_best *partials;         // [gridDim.x] per-CTA (value, global index)
+  long long index_base;        // global index of candidate 0 of this launch
+};
+
 // ---- internal entry points (one per .cu) ------------------------------------------------
 int ombo_refresh_impl(ombo_ctx *ctx, const ombo_gp_spec *spec, void *state, cudaStream_t s);
 int ombo_nlml_grad_impl(ombo_ctx *ctx, const ombo_gp_spec *spec, void *state, double *out_host, cudaStream_t s);
 int ombo_posterior_fp64(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, long long m,
                         double *mu, double *var, bool want_var, cudaStream_t s);
+// fuse_req != NULL asks for the fused 2-D EHVI + arg-max epilogue; *fused reports whether the launch did it (only
+// the f8c kernel can, and only while the stripes fit beside its operand rings) -- if not, mu / var were written
+// and the caller runs K4 as usual
 int ombo_posterior_fast(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, long long m,
-                        double *mu, double *var, bool want_var, cudaStream_t s);
+                        double *mu, double *var, bool want_var, cudaStream_t s,
+                        const FuseAcq *fuse_req = nullptr, int *fused = nullptr);
 int ombo_posterior_fast8(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, long long m,
-                         double *mu, double *var, cudaStream_t s);
+                         double *mu, double *var, cudaStream_t s,
+                         const FuseAcq *fuse_req = nullptr, int *fused = nullptr);
+// merges n_partials per-block (value, index) pairs in ctx->ws_partial with the running best
+int ombo_argmax_merge(ombo_ctx *ctx, int n_partials, ombo_best *best_dev, cudaStream_t s);
 int ombo_fast_path_built();
 int ombo_acquire(ombo_ctx *ctx, const ombo_acq *acq, int n_gp, const double *mu, const double *var,
                  long long m, long long ld, long long index_base, double *out_acq,

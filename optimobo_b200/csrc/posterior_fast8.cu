@@ -41,6 +41,7 @@
 #include <vector>
 
 #include "umma.cuh"
+#include "acq_math.cuh"
 
 #define F8_HI_BYTES 16384   // 128 rows x 64 fp16 (SWIZZLE_128B)
 #define F8_P8_BYTES 8192    // 128 rows x 64 e4m3 (SWIZZLE_64B)
@@ -111,7 +112,7 @@ struct F8Maps {            // tensor maps of the three B planes (128-row and 32-
   CUtensorMap hi128, hi32, c1_128, c1_32, c2_128, c2_32, kc;
 };
 
-template <int DP, int R, int GW>
+template <int DP, int R, int GW, bool MATERN>
 __global__ void __launch_bounds__((8 + GW) * 32, 1)
 k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
   constexpr int NSTA = 3, NSTB = 3;
@@ -152,10 +153,18 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
   uint32_t *landed = store_seq + 128;                          // (spare words)
   // the step schedule is staged in shared memory (every role reads a word per step, and with this much shared
   // memory carved out there is next to no L1 left for a global table); very long schedules stay in global memory
-  uint32_t *sched_sm = landed + 4;
+  uint64_t *mu_full = (uint64_t *)(landed + 4);                // [2] fused epilogue: the tile's mean partials are in mu_sm
+  double *red_v = (double *)(mu_full + 2);                     // [4] + [4] per-warp arg-max of the fused epilogue
+  long long *red_i = (long long *)(red_v + 4);
+  uint32_t *sched_sm = (uint32_t *)(red_i + 4);
   const uint32_t *sched = prm.sched_in_smem ? (const uint32_t *)sched_sm : prm.sched;
   if (prm.sched_in_smem)
     for (int i = tid; i < n_steps; i += blockDim.x) sched_sm[i] = __ldg(prm.sched + i);
+  // fused acquisition: stripe bounds of the 2-D EHVI as FP32, behind the schedule
+  const bool fuse = prm.fuse.on != 0;
+  float *ystr = (float *)(sched_sm + (prm.sched_in_smem ? n_steps : 0));
+  if (fuse)
+    for (int i = tid; i < 2 * (prm.fuse.n_pf + 2); i += blockDim.x) ystr[i] = (float)prm.fuse.stripes[i];
 
   if (tid == 0) {
     for (int j = 0; j < DP; ++j) inv_ell[j] = j < d ? 1.0 / prm.gp.ell[j] : 0.0;
@@ -169,6 +178,7 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&t_full[s]), 1); mbar_init(smem_u32(&t_empty[s]), 8);
       mbar_init(smem_u32(&xc_full[s]), 1); mbar_init(smem_u32(&xc_empty[s]), GEN_WARPS);
+      mbar_init(smem_u32(&mu_full[s]), GEN_WARPS);
     }
     for (int s = 0; s < NSL; ++s) { mbar_init(smem_u32(&s_full[s]), 1); mbar_init(smem_u32(&s_empty[s]), GEN_WARPS); }
     fence_mbar_init();
@@ -388,8 +398,14 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
     const int row = quad * 32 + lane;
     uint32_t fph = 0;
     const uint32_t t_empty_leader = mapa_rank(smem_u32(&t_empty[0]), 0);
+    BestPair best;                               // fused acquisition: this thread's running arg-max
+    best.v = -INFINITY; best.i = 0x7fffffffffffffffLL;
     for (long long it = 0; it < n_iter; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
+      const long long cg = tile * FM + row;
+      // model 0's posterior of this candidate: requested now, needed after the tile's last chunk
+      double m0 = 0.0, v0 = 1.0;
+      if (fuse && cg < prm.m) { m0 = __ldg(prm.fuse.mu0 + cg); v0 = __ldg(prm.fuse.var0 + cg); }
       double ss = 0.0;
       for (int si = 0; si < n_steps; ++si) {
         const uint32_t w = sched[si];
@@ -417,10 +433,36 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
           ss += (double)((part[0] + part[1]) + (part[2] + part[3]));
         }
       }
-      const long long cg = tile * FM + row;
-      if (cg < prm.m) {
-        double v = prm.gp.sigma_f2 - ss * prm.gp.bscale[2];
-        prm.var_out[cg] = fmax(v, prm.gp.var_floor) + prm.gp.sigma_n2;
+      const double var = fmax(prm.gp.sigma_f2 - ss * prm.gp.bscale[2], prm.gp.var_floor) + prm.gp.sigma_n2;
+      if (!fuse) {
+        if (cg < prm.m) prm.var_out[cg] = var;
+      } else {
+        // K4 + K5 on the epilogue warps: the generators publish the tile's mean partials (same summation order
+        // as their own mu_out store, so the fused and the unfused launch see the same FP32 mean)
+        const int b = (int)(it & 1);
+        mbar_wait_sleep(smem_u32(&mu_full[b]), (uint32_t)(it >> 1) & 1, 64);
+        const float *mub = mu_sm + (size_t)b * 4 * FM;
+        const float mu1 = (mub[row] + mub[FM + row]) + (mub[2 * FM + row] + mub[3 * FM + row]);
+        if (cg < prm.m) {
+          const int P = prm.fuse.n_pf;
+          const float r = ehvi2d_value<float>((float)m0, mu1, (float)v0, (float)var, ystr, ystr + (P + 2), P,
+                                              prm.fuse.exact != 0, prm.fuse.c00, prm.fuse.c01);
+          if (prm.fuse.out_acq) prm.fuse.out_acq[cg] = (double)r;
+          const double val = isnan(r) ? -INFINITY : (double)r;
+          const long long gi = prm.fuse.index_base + cg;
+          if (better(val, gi, best.v, best.i)) { best.v = val; best.i = gi; }
+        }
+      }
+    }
+    if (fuse) {
+      best = warp_best(best);
+      if (lane == 0) { red_v[quad] = best.v; red_i[quad] = best.i; }
+      named_bar_sync(8, 128);
+      if (quad == 0 && lane == 0) {
+        for (int q = 1; q < 4; ++q)
+          if (better(red_v[q], red_i[q], best.v, best.i)) { best.v = red_v[q]; best.i = red_i[q]; }
+        prm.fuse.partials[blockIdx.x].value = best.v;
+        prm.fuse.partials[blockIdx.x].index = best.i;
       }
     }
   } else {
@@ -444,7 +486,8 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
     const int r16 = ((lane >> 1) & 3) * 2 + ((lane >> 3) & 1) + 8 * (lane >> 4);
     const int row0 = 16 * R * rg + r16;
     static_assert(GW * R == 32, "generator rows must cover the tile");
-    const bool matern = (prm.gp.kernel == OMBO_KERNEL_MATERN52);
+    // (the kernel function is a template parameter: a run-time branch per row splits the block body into basic
+    // blocks and the scheduler cannot interleave one row's MUFU chain with the next row's FFMA2s / conversions)
     constexpr int ROWS = R;
     uint32_t off_hi[ROWS], off_c8[ROWS];
 #pragma unroll
@@ -531,7 +574,7 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
 #pragma unroll
             for (int rr = 0; rr < ROWS; ++rr) {
               float2 kv[4];
-              if (matern) {
+              if (MATERN) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   float2 rad, ex;
@@ -599,6 +642,11 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
       for (int rr = 0; rr < ROWS; ++rr) {
         const float m = mu_acc[rr] + __shfl_xor_sync(0xffffffffu, mu_acc[rr], 1);
         if (!gbit) mub[qq * FM + row0 + 16 * rr] = m;
+      }
+      if (fuse) {                                  // the epilogue warps finish the mean themselves; no mu_out store
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&mu_full[b]));
+        continue;
       }
       named_bar_sync(1 + rg, 128);
       const int tg = qq * 32 + lane;
@@ -760,14 +808,21 @@ static int make_plane_map(CUtensorMap *map, const void *base, int n_pad, int esz
   return OMBO_OK;
 }
 
-template <int DP, int R, int GW>
+// dynamic shared memory without the step schedule and the fused stripes: operand rings, candidate coordinates,
+// train slices, mean partials, barriers + tables (see the carve-up at the top of the kernel), alignment slack
+static size_t f8_smem_base(int DP) {
+  return (size_t)6 * STAGE_BYTES + 2 * (size_t)DP * FM * 4 + (size_t)F8_NSL * (DP + 2) * FK * 4 + 8 * FM * 4 + 16 +
+         34 * 8 + 16 * 8 + 128 * 4 + 16 + 2 * 8 + 8 * 8 + 1024;
+}
+
+template <int DP, int R, int GW, bool MATERN>
 static int launch_fast8(ombo_ctx *ctx, const F8Maps &maps, FastParams prm, int grid, cudaStream_t s) {
-  size_t smem = (size_t)6 * STAGE_BYTES + 2 * (size_t)DP * FM * 4 + (size_t)F8_NSL * (DP + 2) * FK * 4 +
-                      8 * FM * 4 + 16 + 34 * 8 + 16 * 8 + 128 * 4 + 16 + 1024;
+  size_t smem = f8_smem_base(DP);
   prm.sched_in_smem = smem + (size_t)prm.n_steps * 4 <= 227 * 1024 ? 1 : 0;
   if (prm.sched_in_smem) smem += (size_t)prm.n_steps * 4;
+  if (prm.fuse.on) smem += (size_t)2 * (prm.fuse.n_pf + 2) * 4;
   // per device, not per process: the attribute belongs to the (function, device) pair
-  OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast8<DP, R, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast8<DP, R, GW, MATERN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(ctx, s);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -779,13 +834,14 @@ static int launch_fast8(ombo_ctx *ctx, const F8Maps &maps, FastParams prm, int g
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  OMBO_CUDA(cudaLaunchKernelEx(&cfg, k_posterior_fast8<DP, R, GW>, maps, prm));
+  OMBO_CUDA(cudaLaunchKernelEx(&cfg, k_posterior_fast8<DP, R, GW, MATERN>, maps, prm));
   return OMBO_OK;
 }
 
 // mu / var of one GP whose planes are in the f8c format (gp.flags & OMBO_GP_F8C_PLANES), d <= 12
 int ombo_posterior_fast8(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, long long m, double *mu, double *var,
-                         cudaStream_t s) {
+                         cudaStream_t s, const FuseAcq *fuse_req, int *fused) {
+  if (fused) *fused = 0;
   const long long tiles = (m + FM - 1) / FM;
   F8Maps maps;
   const unsigned char *c1 = (const unsigned char *)gp.blo, *c2 = c1 + (size_t)gp.n_pad * gp.n_pad;
@@ -830,6 +886,21 @@ int ombo_posterior_fast8(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lo
   }
   prm.sched = ctx->f8_sched;
   prm.n_steps = ctx->f8_sched_len;
+  prm.fuse.on = 0;
+  if (fuse_req) {
+    // fused 2-D EHVI + arg-max: only while the stripes fit beside everything else in shared memory
+    const int dp = gp.d <= 2 ? 2 : (gp.d + 1) / 2 * 2;
+    size_t need = f8_smem_base(dp) + (size_t)2 * (fuse_req->n_pf + 2) * 4;
+    if (need + (size_t)prm.n_steps * 4 <= 227 * 1024) need += (size_t)prm.n_steps * 4;
+    if (need <= 227 * 1024) {
+      rc = ombo_ws_reserve(&ctx->ws_partial, &ctx->ws_partial_bytes, (size_t)grid * sizeof(ombo_best));
+      if (rc) return rc;
+      prm.fuse = *fuse_req;
+      prm.fuse.on = 1;
+      prm.fuse.partials = (ombo_best *)ctx->ws_partial;
+      if (fused) *fused = grid;
+    }
+  }
   if (gp.n_pad > 512) {                          // more than two chunks: generated K* blocks are cached in L2 for later chunks
     rc = ombo_ws_reserve(&ctx->ws_scratch, &ctx->ws_scratch_bytes, (size_t)grid * (gp.n_pad / FK) * STAGE_BYTES);
     if (rc) return rc;
@@ -839,8 +910,10 @@ int ombo_posterior_fast8(ombo_ctx *ctx, const GpDev &gp, const PoolDev &pool, lo
   }
   const int d = gp.d;
   const bool gw16 = ctx->knobs.fast_gen_warps == 16;
+  const bool mat = gp.kernel == OMBO_KERNEL_MATERN52;
 #define F8_DISPATCH(DPV)                                                                     \
-  rc = gw16 ? launch_fast8<DPV, 2, 16>(ctx, maps, prm, grid, s) : launch_fast8<DPV, 4, 8>(ctx, maps, prm, grid, s)
+  rc = gw16 ? (mat ? launch_fast8<DPV, 2, 16, true>(ctx, maps, prm, grid, s) : launch_fast8<DPV, 2, 16, false>(ctx, maps, prm, grid, s)) \
+            : (mat ? launch_fast8<DPV, 4, 8, true>(ctx, maps, prm, grid, s) : launch_fast8<DPV, 4, 8, false>(ctx, maps, prm, grid, s))
   if (d <= 2) { F8_DISPATCH(2); }
   else if (d <= 4) { F8_DISPATCH(4); }
   else if (d <= 6) { F8_DISPATCH(6); }

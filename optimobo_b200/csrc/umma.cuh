@@ -249,6 +249,7 @@ struct FastParams {
   int n_steps;
   int sched_in_smem;           // set by the launcher when the table fits beside the operand rings
   long long *trace;  // optional event trace of CTA 0 (OMBO_FAST_PROFILE=2): [8 roles][F8_TRACE_N] of (clock << 8 | code)
+  FuseAcq fuse;      // f8c kernel only
 };
 
 

@@ -487,6 +487,53 @@ def test_full_path_fast_ehvi_selection():
     assert a_r[fast.best_index] >= a_r[order[0]] * (1 - 5e-3)
 
 
+@pytest.mark.parametrize("n,d,m", [(128, 10, 63), (512, 12, 3000), (1024, 10, 148 * 128 + 5), (1024, 10, (1 << 20) + 3)])
+def test_fused_acquisition_epilogue_matches_k4(n, d, m):
+    """K4 + K5 fused behind the last model's K2 (f8c kernel, 2-D EHVI, no posterior asked for) against the unfused
+    launch sequence, which runs when the posterior is also requested: the same FP32 EHVI function on the same mean
+    and variance, so values and selection must be identical (util_functions.py:136-167 end to end)."""
+    if not _cabi.fast_path_available():
+        pytest.skip("fast path not built")
+    X, Y, ells, sf2 = make_problem(n, d)
+    models = [ob.GPModel(X, Y[:, i], ells[i], sf2[i], device=DEV) for i in range(2)]
+    assert [g.plane_format for g in models] == ["f8c", "f8c"]
+    PF, r = ob.host_prep.calc_pf(Y), Y.max(0)
+    spec = ob.spec_ehvi(r, PF, ob.host_prep.cached_samples(2, 5, seed=0), "exact")
+    for pool in (ob.CandidatePool.counter(m, np.zeros(d), np.ones(d), seed=3),
+                 ob.CandidatePool.explicit(np.random.default_rng(1).random((min(m, 20000), d)), device=DEV)):
+        before = _cabi.Context.get(0).launch_count()
+        fused = ob.score(models, spec, pool, precision="fast", want_acq=True)
+        n_fused = _cabi.Context.get(0).launch_count() - before
+        plain = ob.score(models, spec, pool, precision="fast", want_acq=True, want_posterior=True)
+        n_plain = _cabi.Context.get(0).launch_count() - before - n_fused
+        only = ob.score(models, spec, pool, precision="fast")
+        assert n_fused < n_plain                       # k_acquire did not run
+        np.testing.assert_array_equal(fused.acq.cpu().numpy(), plain.acq.cpu().numpy())
+        assert (fused.best_index, fused.best_value) == (plain.best_index, plain.best_value) == (only.best_index, only.best_value)
+        ref = ob.score(models, spec, pool, precision="fp64", want_acq=True)
+        a_r = ref.acq.cpu().numpy()
+        np.testing.assert_allclose(fused.acq.cpu().numpy(), a_r, rtol=5e-3, atol=2e-3 * np.abs(a_r).max())
+
+
+def test_fused_acquisition_falls_back_on_a_long_front():
+    """A front whose stripes do not fit beside the operand rings runs the unfused sequence (same results)."""
+    if not _cabi.fast_path_available():
+        pytest.skip("fast path not built")
+    n, d, m = 1024, 12, 4096
+    X, Y, ells, sf2 = make_problem(n, d)
+    t = np.linspace(0.0, 1.0, n)
+    Y = np.column_stack([t, 1.0 - t]) + 1e-3 * Y          # every training point on the first front
+    models = [ob.GPModel(X, Y[:, i], ells[i], sf2[i], device=DEV) for i in range(2)]
+    PF, r = ob.host_prep.calc_pf(Y), Y.max(0) + 0.1
+    assert len(PF) > 900
+    spec = ob.spec_ehvi(r, PF, ob.host_prep.cached_samples(2, 5, seed=0), "exact")
+    pool = ob.CandidatePool.counter(m, np.zeros(d), np.ones(d), seed=3)
+    a = ob.score(models, spec, pool, precision="fast", want_acq=True)
+    b = ob.score(models, spec, pool, precision="fast", want_acq=True, want_posterior=True)
+    np.testing.assert_array_equal(a.acq.cpu().numpy(), b.acq.cpu().numpy())
+    assert (a.best_index, a.best_value) == (b.best_index, b.best_value)
+
+
 # ------------------------------------------------------------------------------------------
 # section 8f-1: marginal likelihood + gradient on the device (hyper-parameter fit)
 # ------------------------------------------------------------------------------------------
