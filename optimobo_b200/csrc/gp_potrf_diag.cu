@@ -35,10 +35,12 @@ __global__ void __launch_bounds__(64) k_potrf_diag(double *__restrict__ A, int l
     if (t > j) a[j] = a[j] / piv;
     col[t] = a[j];                 // column j of L (entries t < j are never read)
     __syncthreads();
+    // rows below the pivot: the whole remaining row is updated, also its entries above the diagonal (k > t) -- they
+    // are never read (the store below writes zeros there), and leaving the per-element predicate out removes two
+    // FSELs and a compare per DFMA from a loop that two warps execute back to back
     if (t > j) {
 #pragma unroll
-      for (int k = j + 1; k < NB; ++k)
-        if (k <= t) a[k] -= a[j] * col[k];
+      for (int k = j + 1; k < NB; ++k) a[k] -= a[j] * col[k];
     }
   }
 #pragma unroll
@@ -53,9 +55,9 @@ __global__ void __launch_bounds__(64) k_potrf_diag(double *__restrict__ A, int l
 #pragma unroll
   for (int i = 0; i < NB; ++i) {
     double sacc = (i == t) ? 1.0 : 0.0;
+    // x[k] = 0 for k < t, so those terms need no predicate (same sum, same order for the entries that count)
 #pragma unroll
-    for (int k = 0; k < i; ++k)
-      if (k >= t) sacc -= Ls[i][k] * x[k];
+    for (int k = 0; k < i; ++k) sacc -= Ls[i][k] * x[k];
     x[i] = (i >= t) ? sacc / Ls[i][i] : 0.0;
   }
 #pragma unroll

@@ -522,7 +522,7 @@ def test_fused_acquisition_falls_back_on_a_long_front():
     n, d, m = 1024, 12, 4096
     X, Y, ells, sf2 = make_problem(n, d)
     t = np.linspace(0.0, 1.0, n)
-    Y = np.column_stack([t, 1.0 - t]) + 1e-3 * Y          # every training point on the first front
+    Y = np.column_stack([t, 1.0 - t]) + 1e-5 * Y          # every training point on the first front
     models = [ob.GPModel(X, Y[:, i], ells[i], sf2[i], device=DEV) for i in range(2)]
     PF, r = ob.host_prep.calc_pf(Y), Y.max(0) + 0.1
     assert len(PF) > 900
