@@ -5,7 +5,7 @@ large candidate pools as hand-written sm_100a CUDA behind a C ABI (include/optim
 dropped in under the reference's Python surface.  See DESIGN.md / INTEGRATION.md.
 """
 from . import _cabi, device_prep, host_prep, scalarisations  # noqa: F401
-from .gp import GPModel  # noqa: F401
+from .gp import GPModel, refresh_models  # noqa: F401
 from .acquisition import (  # noqa: F401
     AcquisitionSpec, CandidatePool, EHVI, EHVI_3D, acquire_from_posterior, consraint_ei, evaluate,
     expected_decomposition,

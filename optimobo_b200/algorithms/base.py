@@ -16,6 +16,7 @@ from __future__ import annotations
 import time
 
 import numpy as np
+import torch
 
 from .. import device_prep, host_prep
 from ..acquisition import CandidatePool, propose
@@ -104,6 +105,31 @@ class PoolOptimiserBase:
         self._t_fit = getattr(self, "_t_fit", 0.0) + (t1 - t0)
         self._t_refresh = getattr(self, "_t_refresh", 0.0) + (time.perf_counter() - t1)
         return model
+
+    def _fit_models(self, X, columns):
+        """One surrogate per column of `columns` (objectives / constraints), fitted and refreshed CONCURRENTLY: a fit
+        is a chain of small dependent launches (K3 per likelihood evaluation) that leaves the GPU mostly idle, so the
+        models' chains overlap on separate streams, one host thread each (see gp.refresh_models)."""
+        cols = [np.asarray(c) for c in columns]
+        if len(cols) <= 1 or not torch.cuda.is_available():
+            return [self._fit_model(X, c) for c in cols]
+        from concurrent.futures import ThreadPoolExecutor
+        dev = torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+        cur = torch.cuda.current_stream(dev)
+        streams = [torch.cuda.Stream(dev) for _ in cols]
+        for st in streams:
+            st.wait_stream(cur)
+
+        def work(arg):
+            c, st = arg
+            with torch.cuda.device(dev), torch.cuda.stream(st):
+                return self._fit_model(X, c)
+
+        with ThreadPoolExecutor(len(cols)) as ex:
+            models = list(ex.map(work, zip(cols, streams)))
+        for st in streams:
+            cur.wait_stream(st)
+        return models
 
     def _precision_for(self, models):
         from ..acquisition import resolve_precision

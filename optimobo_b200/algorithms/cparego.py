@@ -111,7 +111,7 @@ class _ConstrainedParEGO(PoolOptimiserBase):
                 model_input = Xsample[sel]
                 agg_model = self._fit_model(model_input, agg[sel])
                 if constrained_acquisition:
-                    constraint_models = [self._fit_model(model_input, gsample[sel, c]) for c in range(gsample.shape[1])]
+                    constraint_models = self._fit_models(model_input, [gsample[sel, c] for c in range(gsample.shape[1])])
                     current_best = self.select_current_best(feas_idx, inf_idx, agg, gsample)
                     next_X, _ = self._propose([agg_model] + constraint_models,
                                               spec_constrained_ei(current_best, len(constraint_models)))

@@ -29,7 +29,7 @@ class EMO(PoolOptimiserBase):
         for _ in range(budget):
             self._update_bounds(ysample)
             hypervolume_convergence.append(self._hypervolume(ysample))
-            models = [self._fit_model(Xsample, ysample[:, i]) for i in range(self.n_obj)]
+            models = self._fit_models(Xsample, [ysample[:, i] for i in range(self.n_obj)])
             cells = self.decompose_into_cells(self._calc_pf(ysample))
             X_next, _ = self._propose(models, spec_hv_poi(cells))
             y_next = self._objective_function(problem, X_next)

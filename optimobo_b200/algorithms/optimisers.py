@@ -26,7 +26,7 @@ class MultiSurrogateOptimiser(PoolOptimiserBase):
         for _ in range(budget):
             self._update_bounds(ysample, acquisition_func)
             hypervolume_convergence.append(self._hypervolume(ysample))
-            models = [self._fit_model(Xsample, ysample[:, i]) for i in range(problem.n_obj)]
+            models = self._fit_models(Xsample, [ysample[:, i] for i in range(problem.n_obj)])
             ref_dir = np.asarray(ref_dirs[self.rng.integers(0, len(ref_dirs))])
             if acquisition_func is None:
                 pf = self._calc_pf(ysample)

@@ -50,6 +50,12 @@ int ombo_ctx_create(int device, ombo_ctx **out) {
                    prop.major, prop.minor);
     return OMBO_ERR_UNSUPPORTED;
   }
+  {   // stream-ordered allocations (the likelihood workspace of concurrent fits) keep their blocks across calls
+    cudaMemPool_t mp;
+    unsigned long long keep = ~0ull;
+    OMBO_CUDA(cudaDeviceGetDefaultMemPool(&mp, device));
+    OMBO_CUDA(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   ombo_ctx *c = new ombo_ctx();
   memset(c, 0, sizeof(*c));
   c->device = device;

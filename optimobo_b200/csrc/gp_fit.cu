@@ -123,9 +123,11 @@ int ombo_nlml_grad_impl(ombo_ctx *ctx, const ombo_gp_spec *sp, void *state, doub
   const int n_blocks = gg.x * gg.y;
   // workspace: W (np x np) + partials + out
   size_t want = (size_t)np * np * 8 + (size_t)n_blocks * (OMBO_MAX_DIM + 1) * 8 + 64 * 8;
-  rc = ombo_ws_reserve(&ctx->ws_scratch, &ctx->ws_scratch_bytes, want);
-  if (rc) return rc;
-  double *W = (double *)ctx->ws_scratch;
+  // stream-ordered allocation (the device's default pool keeps freed blocks: ombo_ctx_create raises its release
+  // threshold), not the context's scratch: likelihood evaluations of different GPs run concurrently on different
+  // streams and host threads (one fit per objective), and each needs its own W
+  double *W = nullptr;
+  OMBO_CUDA(cudaMallocAsync((void **)&W, want, s));
   double *partial = W + (size_t)np * np;
   double *out = partial + (size_t)n_blocks * (OMBO_MAX_DIM + 1);
   k_kinv_minus_aat<<<dim3(np / 64, np / 64), 256, 0, s>>>(Linv, alpha, np, W);
@@ -134,6 +136,7 @@ int ombo_nlml_grad_impl(ombo_ctx *ctx, const ombo_gp_spec *sp, void *state, doub
   ctx->launches += 3;
   OMBO_CUDA(cudaGetLastError());
   OMBO_CUDA(cudaMemcpyAsync(out_host, out, (size_t)(d + 2) * 8, cudaMemcpyDeviceToHost, s));
+  OMBO_CUDA(cudaFreeAsync(W, s));
   OMBO_CUDA(cudaStreamSynchronize(s));
   return OMBO_OK;
 }

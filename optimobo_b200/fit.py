@@ -60,10 +60,11 @@ def fit_hyperparameters(X, y, kernel="matern52", max_f_eval=1000, jitter=1e-8, i
     return np.exp(theta[1:]), float(np.exp(theta[0]))
 
 
-def fit_hyperparameters_device(X, y, kernel="matern52", max_f_eval=1000, jitter=1e-8, init=None, device="cuda:0"):
+def fit_hyperparameters_device(X, y, kernel="matern52", max_f_eval=1000, jitter=1e-8, init=None, device="cuda:0",
+                               info=None):
     """Same optimisation with every likelihood / gradient evaluation on the GPU
     (`ombo_gp_nlml_grad`: K3 refresh + K^-1 + gradient reduction, FP64); scipy's L-BFGS-B drives it from
-    the host.  Returns (lengthscale (d,), variance)."""
+    the host.  Returns (lengthscale (d,), variance); `info` (a dict) receives scipy's evaluation count `nfev`."""
     import ctypes as C
 
     import torch
@@ -96,5 +97,7 @@ def fit_hyperparameters_device(X, y, kernel="matern52", max_f_eval=1000, jitter=
 
     res = minimize(fun, theta0, jac=True, method="L-BFGS-B", bounds=[(-12.0, 14.0)] + [(-7.0, 9.0)] * d,
                    options=dict(maxfun=max_f_eval))
+    if info is not None:
+        info["nfev"] = int(res.nfev)
     theta = res.x if np.isfinite(res.fun) and res.fun < 1e24 else theta0
     return np.exp(theta[1:]), float(np.exp(theta[0]))

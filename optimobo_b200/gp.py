@@ -195,3 +195,38 @@ class GPModel:
         return cls(np.asarray(gpy_model.X), np.asarray(gpy_model.Y).reshape(-1),
                    np.asarray(kern.lengthscale), float(np.asarray(kern.variance).reshape(-1)[0]),
                    noise=float(np.asarray(gpy_model.Gaussian_noise.variance).reshape(-1)[0]), device=device)
+
+
+_REFRESH_STREAMS = {}
+
+
+def refresh_models(models):
+    """Refreshes several GPs of one device concurrently.  K3 is a chain of small dependent launches (16 diagonal
+    blocks of one CTA each at n = 1024) that leaves most SMs idle, so the models' chains overlap on separate streams:
+    2 GPs at n = 1024 take about the time of one.  One host thread per model, because the C entry synchronises its
+    stream to read the positive-definiteness flag (ctypes drops the GIL for the call).  State blobs are per model, the
+    context holds no refresh workspace, so the calls share nothing but the launch counter."""
+    models = list(models)
+    if len(models) <= 1 or len({m.device for m in models}) != 1:
+        for m in models:
+            m.refresh()
+        return models
+    from concurrent.futures import ThreadPoolExecutor
+    dev = models[0].device
+    pool = _REFRESH_STREAMS.setdefault(dev, [])
+    while len(pool) < len(models):
+        pool.append(torch.cuda.Stream(dev))
+    cur = torch.cuda.current_stream(dev)
+    for st in pool[: len(models)]:
+        st.wait_stream(cur)
+
+    def work(arg):
+        m, st = arg
+        with torch.cuda.device(dev), torch.cuda.stream(st):
+            m.refresh()
+
+    with ThreadPoolExecutor(len(models)) as ex:
+        list(ex.map(work, zip(models, pool)))
+    for st in pool[: len(models)]:
+        cur.wait_stream(st)
+    return models

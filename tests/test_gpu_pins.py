@@ -216,3 +216,15 @@ def test_precision_auto_everywhere():
     assert idx == a.best_index
     with pytest.raises(ValueError, match="precision"):
         ob.score(models, spec, pool, precision="fp32")
+
+
+def test_refresh_models_concurrent_matches_serial():
+    """gp.refresh_models (one stream + host thread per model) leaves the same state blobs as serial refreshes."""
+    X, Y, ells, sf2 = make_problem(700, 7)
+    a = [ob.GPModel(X, Y[:, i], ells[i], sf2[i], device=DEV) for i in range(2)]
+    b = [ob.GPModel(X, Y[:, i], ells[i], sf2[i], device=DEV, refresh=False) for i in range(2)]
+    ob.refresh_models(b)
+    torch.cuda.synchronize()
+    for ma, mb in zip(a, b):
+        assert mb.refreshed and mb.plane_format == ma.plane_format
+        assert torch.equal(ma.state, mb.state)
