@@ -233,7 +233,16 @@ static int score_pass(ombo_ctx *ctx, const ombo_gp *gps, int n_gp, const ombo_po
     ld = count;
   }
   int fused = 0;
-  for (int g = 0; g < n_gp; ++g) {
+  // K4 + K5 fused behind the last K2 launch of the pass (fast mode, 2-D EHVI, nobody asked for the posterior itself):
+  // the f8c kernel's epilogue warps evaluate the EHVI from registers and keep a per-CTA arg-max, so that model's
+  // mu / var are never written and k_acquire does not run (ehvi2d_value is the same function either way).  The
+  // launch that carries the acquisition must be a variance launch: model 1 in exact semantics, model 0 in reference
+  // semantics (which reads only model 0's variance, so model 1 goes first through the mean-only kernel).
+  const bool fuse_candidate = precision == OMBO_PREC_FAST && n_gp == 2 && acq->kind == OMBO_ACQ_EHVI2D && !out_mu &&
+                              !out_var && !ctx->knobs.no_fuse && !ctx->knobs.acq_fp64 && (out_acq || best_dev);
+  const int fuse_g = fuse_candidate ? (acq->semantics == OMBO_SEM_EXACT ? 1 : 0) : -1;
+  for (int step = 0; step < n_gp; ++step) {
+    const int g = fuse_g == 0 ? n_gp - 1 - step : step;          // the fused model's launch comes last
     GpDev gd = gp_dev_view(gps[g]);
     // K2 is skipped for GPs whose variance nothing reads (the caller did not ask for the posterior and
     // the acquisition ignores it): reference-semantics EHVI / EHVI_3D / expected decomposition scale
@@ -251,18 +260,17 @@ static int score_pass(ombo_ctx *ctx, const ombo_gp *gps, int n_gp, const ombo_po
         default: want_var = true;
       }
     }
-    // K4 + K5 fused behind the last model's K2 (fast mode, 2-D EHVI, nobody asked for the posterior itself): the
-    // f8c kernel's epilogue warps evaluate the EHVI from registers and keep a per-CTA arg-max, so this model's
-    // mu / var are never written and k_acquire does not run (ehvi2d_value is the same function either way)
     FuseAcq fq;
-    const bool try_fuse = precision == OMBO_PREC_FAST && g == n_gp - 1 && n_gp == 2 && acq->kind == OMBO_ACQ_EHVI2D &&
-                          want_var && !out_mu && !out_var && !ctx->knobs.no_fuse && !ctx->knobs.acq_fp64 &&
-                          (out_acq || best_dev);
+    const bool try_fuse = g == fuse_g && step == n_gp - 1 && want_var;
     if (try_fuse) {
+      const int o = 1 - g;
       memset(&fq, 0, sizeof(fq));
       fq.n_pf = acq->n_pf; fq.exact = acq->semantics == OMBO_SEM_EXACT;
       fq.c00 = (float)acq->cache_c00; fq.c01 = (float)acq->cache_c01;
-      fq.mu0 = mu; fq.var0 = var; fq.stripes = acq->stripes;
+      fq.self_model = g;
+      fq.mu_other = mu + (size_t)o * ld;
+      fq.var_other = fq.exact ? var + (size_t)o * ld : nullptr;      // reference semantics never reads model 1's variance
+      fq.stripes = acq->stripes;
       fq.out_acq = out_acq ? out_acq + first : nullptr;
       fq.index_base = pd.index_base;
     }

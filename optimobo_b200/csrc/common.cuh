@@ -172,13 +172,16 @@ struct PoolDev {
   double lo[OMBO_MAX_DIM], span[OMBO_MAX_DIM];
 };
 
-// f8c kernel: 2-D EHVI and the per-CTA arg-max evaluated by the epilogue warps of the LAST model's launch (K4 + K5
-// fused behind K2: the model's mu / var never leave the SM, the other model's come from the posterior workspace)
+// f8c kernel: 2-D EHVI and the per-CTA arg-max evaluated by the epilogue warps of the last launch of a pass (K4 + K5
+// fused behind K2: that model's mu / var never leave the SM, the other model's come from the posterior workspace).
+// Exact semantics: model 0 first, model 1 carries the acquisition.  Reference semantics reads only model 0's variance
+// (util_functions.py:233), so model 1 runs first in the mean-only kernel and model 0's launch carries it.
 struct FuseAcq {
   int on;                      // 0: plain posterior launch (mu_out / var_out written)
   int n_pf, exact;             // stripes y1[0..P+1], y2[0..P+1]; semantics flag of ehvi2d_value
   float c00, c01;              // reference semantics: flattened sample covariance entries
-  const double *mu0, *var0;    // posterior of model 0 for the same candidates
+  int self_model;              // which objective this launch computes (0 or 1)
+  const double *mu_other, *var_other;   // posterior of the other model for the same candidates (var_other may be NULL)
   const double *stripes;       // device, 2 (P + 2) doubles
   double *out_acq;             // optional per-candidate values
   ombo_best *partials;         // [gridDim.x] per-CTA (value, global index)

@@ -403,9 +403,12 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
     for (long long it = 0; it < n_iter; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
       const long long cg = tile * FM + row;
-      // model 0's posterior of this candidate: requested now, needed after the tile's last chunk
-      double m0 = 0.0, v0 = 1.0;
-      if (fuse && cg < prm.m) { m0 = __ldg(prm.fuse.mu0 + cg); v0 = __ldg(prm.fuse.var0 + cg); }
+      // the other model's posterior of this candidate: requested now, needed after the tile's last chunk
+      double mo = 0.0, vo = 1.0;
+      if (fuse && cg < prm.m) {
+        mo = __ldg(prm.fuse.mu_other + cg);
+        if (prm.fuse.var_other) vo = __ldg(prm.fuse.var_other + cg);
+      }
       double ss = 0.0;
       for (int si = 0; si < n_steps; ++si) {
         const uint32_t w = sched[si];
@@ -442,10 +445,12 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
         const int b = (int)(it & 1);
         mbar_wait_sleep(smem_u32(&mu_full[b]), (uint32_t)(it >> 1) & 1, 64);
         const float *mub = mu_sm + (size_t)b * 4 * FM;
-        const float mu1 = (mub[row] + mub[FM + row]) + (mub[2 * FM + row] + mub[3 * FM + row]);
+        const float mu_s = (mub[row] + mub[FM + row]) + (mub[2 * FM + row] + mub[3 * FM + row]);
         if (cg < prm.m) {
           const int P = prm.fuse.n_pf;
-          const float r = ehvi2d_value<float>((float)m0, mu1, (float)v0, (float)var, ystr, ystr + (P + 2), P,
+          const bool s0 = prm.fuse.self_model == 0;
+          const float r = ehvi2d_value<float>(s0 ? mu_s : (float)mo, s0 ? (float)mo : mu_s, s0 ? (float)var : (float)vo,
+                                              s0 ? (float)vo : (float)var, ystr, ystr + (P + 2), P,
                                               prm.fuse.exact != 0, prm.fuse.c00, prm.fuse.c01);
           if (prm.fuse.out_acq) prm.fuse.out_acq[cg] = (double)r;
           const double val = isnan(r) ? -INFINITY : (double)r;

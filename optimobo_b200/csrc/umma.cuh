@@ -29,8 +29,22 @@ __device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
 }
+#ifndef MBAR_SUSPEND_HINT
+#define MBAR_SUSPEND_HINT 0     // 1: try_wait carries a suspend-time hint (the thread sleeps in hardware until the phase flips)
+#endif
 __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
+#if MBAR_SUSPEND_HINT
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(0x989680u)
+      : "memory");
+#else
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -40,6 +54,7 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(bar), "r"(parity)
       : "memory");
+#endif
   return ok;
 }
 // non-blocking probe (try_wait may suspend the thread for a while before it answers)
@@ -61,7 +76,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 // polling warps steal issue slots from the K1 generators: back off between probes
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, unsigned ns) {
+#if MBAR_SUSPEND_HINT
+  while (!mbar_try(bar, parity)) {}
+#else
   while (!mbar_try(bar, parity)) __nanosleep(ns);
+#endif
 }
 // one lane of a CONVERGED warp; unlike `lane == 0` the compiler knows a single thread is active, so
 // tcgen05 / TMA operands stay in uniform registers without a per-instruction waterfall loop

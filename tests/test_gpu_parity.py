@@ -515,6 +515,34 @@ def test_fused_acquisition_epilogue_matches_k4(n, d, m):
         np.testing.assert_allclose(fused.acq.cpu().numpy(), a_r, rtol=5e-3, atol=2e-3 * np.abs(a_r).max())
 
 
+@pytest.mark.parametrize("n,d,m", [(256, 10, 5001), (1024, 10, 148 * 128 + 5)])
+def test_fused_acquisition_epilogue_reference_semantics(n, d, m):
+    """The reference's default EHVI (sigma from model 0's variance only, util_functions.py:163-167, :233): model 1 runs
+    the mean-only kernel first, model 0's launch carries the acquisition.  Against the unfused sequence (both models
+    through the full kernel, whose FP32 mean of model 1 is summed in another order: 1e-6 of the scale) and against
+    the FP64 path."""
+    if not _cabi.fast_path_available():
+        pytest.skip("fast path not built")
+    X, Y, ells, sf2 = make_problem(n, d)
+    models = [ob.GPModel(X, Y[:, i], ells[i], sf2[i], device=DEV) for i in range(2)]
+    PF, r = ob.host_prep.calc_pf(Y), Y.max(0)
+    spec = ob.spec_ehvi(r, PF, ob.host_prep.cached_samples(2, 5, seed=0), "reference")
+    pool = ob.CandidatePool.counter(m, np.zeros(d), np.ones(d), seed=3)
+    before = _cabi.Context.get(0).launch_count()
+    fused = ob.score(models, spec, pool, precision="fast", want_acq=True)
+    n_fused = _cabi.Context.get(0).launch_count() - before
+    plain = ob.score(models, spec, pool, precision="fast", want_acq=True, want_posterior=True)
+    n_plain = _cabi.Context.get(0).launch_count() - before - n_fused
+    only = ob.score(models, spec, pool, precision="fast")
+    assert n_fused < n_plain
+    a_f, a_p = fused.acq.cpu().numpy(), plain.acq.cpu().numpy()
+    np.testing.assert_allclose(a_f, a_p, rtol=1e-4, atol=1e-5 * np.abs(a_p).max())
+    assert (fused.best_index, fused.best_value) == (only.best_index, only.best_value)
+    assert fused.best_value == a_f[fused.best_index] == np.nanmax(a_f)
+    a_r = ob.score(models, spec, pool, precision="fp64", want_acq=True).acq.cpu().numpy()
+    np.testing.assert_allclose(a_f, a_r, rtol=5e-3, atol=2e-3 * np.abs(a_r).max())
+
+
 def test_fused_acquisition_falls_back_on_a_long_front():
     """A front whose stripes do not fit beside the operand rings runs the unfused sequence (same results)."""
     if not _cabi.fast_path_available():

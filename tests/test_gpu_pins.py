@@ -227,4 +227,10 @@ def test_refresh_models_concurrent_matches_serial():
     torch.cuda.synchronize()
     for ma, mb in zip(a, b):
         assert mb.refreshed and mb.plane_format == ma.plane_format
-        assert torch.equal(ma.state, mb.state)
+        for f in ("L", "Linv", "alpha"):             # (the blob also holds scratch fields a refresh never initialises)
+            assert torch.equal(getattr(ma, f), getattr(mb, f)), f
+    pool = ob.CandidatePool.counter(4096, np.zeros(7), np.ones(7), seed=2)
+    for prec in ("fp64", "fast"):
+        ra = ob.score(a, None, pool, precision=prec, want_posterior=True)
+        rb = ob.score(b, None, pool, precision=prec, want_posterior=True)
+        assert torch.equal(ra.mu, rb.mu) and torch.equal(ra.var, rb.var)
