@@ -198,6 +198,7 @@ class GPModel:
 
 
 _REFRESH_STREAMS = {}
+_REFRESH_POOL = None          # host threads are kept: starting two per call costs as much as the overlap saves
 
 
 def refresh_models(models):
@@ -211,7 +212,10 @@ def refresh_models(models):
         for m in models:
             m.refresh()
         return models
-    from concurrent.futures import ThreadPoolExecutor
+    global _REFRESH_POOL
+    if _REFRESH_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _REFRESH_POOL = ThreadPoolExecutor(max_workers=8, thread_name_prefix="ombo-refresh")
     dev = models[0].device
     pool = _REFRESH_STREAMS.setdefault(dev, [])
     while len(pool) < len(models):
@@ -225,8 +229,7 @@ def refresh_models(models):
         with torch.cuda.device(dev), torch.cuda.stream(st):
             m.refresh()
 
-    with ThreadPoolExecutor(len(models)) as ex:
-        list(ex.map(work, zip(models, pool)))
+    list(_REFRESH_POOL.map(work, zip(models, pool)))
     for st in pool[: len(models)]:
         cur.wait_stream(st)
     return models
