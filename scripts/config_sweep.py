@@ -15,8 +15,10 @@ for name, make in T.CONFIGS.items():
     models = [ob.GPModel(X, y, e, s, device=dev) for y, e, s in zip(ys, ells, sf2)]
     pool = ob.CandidatePool.counter(m, lo, hi, seed=1)
     n = len(X)
-    for prec in (("fp64", "fast") if n > 256 else ("fp64",)):
+    for prec in (("fp64", "fast") if n >= 256 else ("fp64",)):
         mm = m if prec == "fast" or n <= 256 else min(m, 1 << 20)
+        if prec == "fast" and n <= 256:
+            mm = 1 << 24                      # C2 in the fast mode: the pool size the round-1 table quotes
         p = ob.CandidatePool.counter(mm, lo, hi, seed=1)
         for _ in range(3):
             ob.score(models, spec, p, precision=prec, sync=False)
