@@ -118,6 +118,30 @@ def test_reference_acquisition_callables_run_unmodified_on_gpmodel(golden):
     np.testing.assert_allclose(batched, one_at_a_time, rtol=1e-6, atol=1e-9 * np.abs(batched).max())
 
 
+def test_unmodified_reference_ehvi_runs_on_gpmodel(golden):
+    """The boundary claim of INTEGRATION.md section B: the reference's OWN `util_functions.EHVI` (util_functions.py:136-167,
+    loaded unmodified through oracle/ref_loader from baseline/_ref, /root/reference or $OPTIMOBO_REF) takes
+    `optimobo_b200.GPModel` objects where it expects GPy models -- one x per call, `model.predict(np.asarray([x]))` --
+    and returns what the batched GPU acquisition returns in reference semantics."""
+    from oracle import ref_loader as R
+    if not R.reference_available():
+        pytest.skip("reference package not reachable (baseline/_ref, /root/reference, $OPTIMOBO_REF)")
+    uf = R.load_reference().util_functions
+    rng = np.random.default_rng(0)
+    X = rng.random((60, 3))
+    Y = np.column_stack([X[:, 0], 1 + X[:, 1:].sum(1) - np.sqrt(X[:, 0])])
+    models = [ob.GPModel(X, Y[:, i], 0.6 * np.ones(3), 1.0 + i, device="cuda:0") for i in range(2)]
+    cache = golden["acq_in_cache2"]
+    PF, r = uf.calc_pf(Y), Y.max(0)                       # the reference's own front
+    np.testing.assert_array_equal(PF, ob.host_prep.calc_pf(Y))
+    Xc = rng.random((40, 3))
+    ref_vals = np.array([float(np.asarray(uf.EHVI(x, models, r, PF, cache)).reshape(-1)[0]) for x in Xc])
+    batched = ob.EHVI(Xc, models, r, PF, cache)           # FP64 mode, reference semantics
+    # np.cov of the affine-mapped samples (util_functions.py:163) rounds differently from var0 * C: 1e-7, as in the goldens
+    np.testing.assert_allclose(batched, ref_vals, rtol=1e-7, atol=1e-9 * np.abs(ref_vals).max())
+    assert int(np.argmax(batched)) == int(np.argmax(ref_vals))
+
+
 def test_score_sharded_single_process_matches_score():
     from optimobo_b200.distributed import score_sharded
     rng = np.random.default_rng(0)
