@@ -19,9 +19,14 @@ __global__ void __launch_bounds__(64) k_potrf_diag(double *__restrict__ A, int l
   __shared__ double pivot;
   const int t = threadIdx.x;
   double *blk = A + ((size_t)kb * NB) * ld + (size_t)kb * NB;
+  // the block travels through shared memory in both directions: a thread reading ITS row straight from global
+  // memory touches 64 different sectors per instruction (row stride ld), 64 times over
+  for (int e = t; e < NB * NB; e += NB) Ls[e / NB][e % NB] = blk[(size_t)(e / NB) * ld + (e % NB)];
+  __syncthreads();
   double a[NB];
 #pragma unroll
-  for (int k = 0; k < NB; ++k) a[k] = blk[(size_t)t * ld + k];
+  for (int k = 0; k < NB; ++k) a[k] = Ls[t][k];
+  __syncthreads();
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
     if (t == j) {
@@ -44,12 +49,9 @@ __global__ void __launch_bounds__(64) k_potrf_diag(double *__restrict__ A, int l
     }
   }
 #pragma unroll
-  for (int k = 0; k < NB; ++k) {
-    const double v = (k <= t) ? a[k] : 0.0;
-    Ls[t][k] = v;
-    blk[(size_t)t * ld + k] = v;
-  }
+  for (int k = 0; k < NB; ++k) Ls[t][k] = (k <= t) ? a[k] : 0.0;
   __syncthreads();
+  for (int e = t; e < NB * NB; e += NB) blk[(size_t)(e / NB) * ld + (e % NB)] = Ls[e / NB][e % NB];
   // inverse: thread t owns COLUMN t of X = L^-1 in registers; L is read from smem by broadcast
   double x[NB];
 #pragma unroll

@@ -153,53 +153,87 @@ __global__ void __launch_bounds__(256) k_syrk_update(double *__restrict__ A, int
 }
 
 // ------------------------------------------------------------------------------------------
-// triangular inverse, 16 columns per CTA
+// triangular inverse, 16 columns per CTA.  X = L^-1, block row by block row:
+//   T = I[ib rows, these columns] - sum_{jb < ib} L[ib][jb] X[jb],   X[ib] = Dinv[ib] T
+// The CTA walks the tile products (ib, jb = kb .. ib-1) and the diagonal product (ib, jb = ib) as ONE sequence of
+// steps and double-buffers their operands with cp.async: the 32 KB tile of L (or of Dinv) and the 64 x 16 tile of X for
+// step s + 1 arrive while step s multiplies (round 1 loaded them between two barriers, and the first column block
+// runs 120 + 16 such steps back to back).  Every sum keeps its order (jb ascending, then t ascending), so the result is
+// bit-identical to the unpipelined kernel.
 #define TC 16
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
+}
+extern __shared__ __align__(16) double trtri_smem[];
 __global__ void __launch_bounds__(256) k_trtri_cols(const double *__restrict__ L, int ld, int nb,
                                                     const double *__restrict__ dinv,
                                                     double *__restrict__ Linv) {
-  __shared__ double Ls[NB][LDS];       // L tile / Dinv tile
-  __shared__ double Xs[NB][TC + 1];    // X rows of block jb / T
+  double (*Lb)[NB][LDS] = (double (*)[NB][LDS])trtri_smem;                              // [2] L tile / Dinv tile
+  double (*Xb)[NB][TC + 1] = (double (*)[NB][TC + 1])(trtri_smem + 2 * NB * LDS);       // [2] X rows of block jb / T
   const int tid = threadIdx.x;
   const int c0 = blockIdx.x * TC;
   const int kb = c0 / NB;
   const int r = tid % NB;          // output row inside the block row
   const int cg = (tid / NB) * 4;   // first of 4 output columns
-  for (int ib = kb; ib < nb; ++ib) {
-    double T[4];
-#pragma unroll
-    for (int v = 0; v < 4; ++v) T[v] = (ib * NB + r == c0 + cg + v) ? 1.0 : 0.0;
-    for (int jb = kb; jb < ib; ++jb) {
-      const double *Lt = L + ((size_t)ib * NB) * ld + (size_t)jb * NB;
-      for (int e = tid; e < NB * NB; e += 256) Ls[e / NB][e % NB] = Lt[(size_t)(e / NB) * ld + (e % NB)];
+  auto issue = [&](int ib, int jb, int buf, bool with_x) {
+    const double *src = jb < ib ? L + ((size_t)ib * NB) * ld + (size_t)jb * NB : dinv + (size_t)ib * NB * NB;
+    const int stride = jb < ib ? ld : NB;
+    for (int e = tid; e < NB * NB; e += 256) cp_async8(&Lb[buf][e / NB][e % NB], src + (size_t)(e / NB) * stride + (e % NB));
+    if (with_x)
       for (int e = tid; e < NB * TC; e += 256)
-        Xs[e / TC][e % TC] = Linv[((size_t)jb * NB + e / TC) * ld + c0 + (e % TC)];
-      __syncthreads();
+        cp_async8(&Xb[buf][e / TC][e % TC], Linv + ((size_t)jb * NB + e / TC) * ld + c0 + (e % TC));
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  int ib = kb, jb = kb, buf = 0;
+  issue(ib, jb, 0, false);
+  double T[4];
+#pragma unroll
+  for (int v = 0; v < 4; ++v) T[v] = (ib * NB + r == c0 + cg + v) ? 1.0 : 0.0;
+  while (ib < nb) {
+    const int nib = jb < ib ? ib : ib + 1, njb = jb < ib ? jb + 1 : kb;
+    const bool has_next = nib < nb;
+    // X[njb] is final unless THIS step is the diagonal product that writes it (only at the very first step)
+    const bool next_x = has_next && njb < nib && !(jb == ib && njb == ib);
+    if (has_next) {
+      issue(nib, njb, buf ^ 1, next_x);
+      asm volatile("cp.async.wait_group 1;\n" ::);
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::);
+    }
+    __syncthreads();
+    if (jb < ib) {
+      if (ib == kb + 1 && jb == kb) {        // the one X tile that could not be prefetched
+        for (int e = tid; e < NB * TC; e += 256)
+          Xb[buf][e / TC][e % TC] = Linv[((size_t)jb * NB + e / TC) * ld + c0 + (e % TC)];
+        __syncthreads();
+      }
 #pragma unroll 8
       for (int t = 0; t < NB; ++t) {
-        double l = Ls[r][t];
+        double l = Lb[buf][r][t];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) T[v] -= l * Xs[t][cg + v];
+        for (int v = 0; v < 4; ++v) T[v] -= l * Xb[buf][t][cg + v];
       }
+    } else {
+      // X_ib = Dinv_ib * T
+#pragma unroll
+      for (int v = 0; v < 4; ++v) Xb[buf][r][cg + v] = T[v];
       __syncthreads();
-    }
-    // X_ib = Dinv_ib * T
-    const double *dv = dinv + (size_t)ib * NB * NB;
-    for (int e = tid; e < NB * NB; e += 256) Ls[e / NB][e % NB] = dv[e];
-#pragma unroll
-    for (int v = 0; v < 4; ++v) Xs[r][cg + v] = T[v];
-    __syncthreads();
-    double o[4] = {0, 0, 0, 0};
+      double o[4] = {0, 0, 0, 0};
 #pragma unroll 8
-    for (int t = 0; t < NB; ++t) {
-      double l = Ls[r][t];
+      for (int t = 0; t < NB; ++t) {
+        double l = Lb[buf][r][t];
 #pragma unroll
-      for (int v = 0; v < 4; ++v) o[v] += l * Xs[t][cg + v];
+        for (int v = 0; v < 4; ++v) o[v] += l * Xb[buf][t][cg + v];
+      }
+#pragma unroll
+      for (int v = 0; v < 4; ++v) Linv[((size_t)ib * NB + r) * ld + c0 + cg + v] = o[v];
+      __threadfence_block();
+#pragma unroll
+      for (int v = 0; v < 4; ++v) T[v] = ((ib + 1) * NB + r == c0 + cg + v) ? 1.0 : 0.0;
     }
-#pragma unroll
-    for (int v = 0; v < 4; ++v) Linv[((size_t)ib * NB + r) * ld + c0 + cg + v] = o[v];
-    __threadfence_block();
     __syncthreads();
+    ib = nib; jb = njb; buf ^= 1;
   }
 }
 
@@ -361,7 +395,9 @@ int ombo_refresh_impl(ombo_ctx *ctx, const ombo_gp_spec *sp, void *state, cudaSt
   ctx->launches += 2;
   int rc = ombo_potrf_lower_impl(ctx, L, np, n, dinv, status, s);
   if (rc) return rc;
-  k_trtri_cols<<<np / TC, 256, 0, s>>>(L, np, nb, dinv, Linv);
+  const size_t sm_tri = (size_t)(2 * NB * LDS + 2 * NB * (TC + 1)) * sizeof(double);
+  OMBO_CUDA(cudaFuncSetAttribute(k_trtri_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_tri));
+  k_trtri_cols<<<np / TC, 256, sm_tri, s>>>(L, np, nb, dinv, Linv);
   // alpha = Linv^T (Linv y); ypad currently lives in alpha
   k_trmv_lower<<<(np + 7) / 8, 256, 0, s>>>(Linv, np, np, alpha, tmp);
   k_trmv_lower_t<<<(np + 31) / 32, dim3(32, 8), 0, s>>>(Linv, np, np, tmp, alpha);
