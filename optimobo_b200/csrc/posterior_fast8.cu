@@ -822,10 +822,10 @@ static size_t f8_smem_base(int DP) {
 
 template <int DP, int R, int GW, bool MATERN>
 static int launch_fast8(ombo_ctx *ctx, const F8Maps &maps, FastParams prm, int grid, cudaStream_t s) {
-  size_t smem = f8_smem_base(DP);
+  // the fused stripes first, then the schedule if it still fits (the same order as the can-fuse test of the caller)
+  size_t smem = f8_smem_base(DP) + (prm.fuse.on ? (size_t)2 * (prm.fuse.n_pf + 2) * 4 : 0);
   prm.sched_in_smem = smem + (size_t)prm.n_steps * 4 <= 227 * 1024 ? 1 : 0;
   if (prm.sched_in_smem) smem += (size_t)prm.n_steps * 4;
-  if (prm.fuse.on) smem += (size_t)2 * (prm.fuse.n_pf + 2) * 4;
   // per device, not per process: the attribute belongs to the (function, device) pair
   OMBO_CUDA(cudaFuncSetAttribute(k_posterior_fast8<DP, R, GW, MATERN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ProfScope prof(ctx, s);
