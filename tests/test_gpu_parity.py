@@ -543,21 +543,31 @@ def test_fused_acquisition_epilogue_reference_semantics(n, d, m):
     np.testing.assert_allclose(a_f, a_r, rtol=5e-3, atol=2e-3 * np.abs(a_r).max())
 
 
-def test_fused_acquisition_falls_back_on_a_long_front():
-    """A front whose stripes do not fit beside the operand rings runs the unfused sequence (same results)."""
+@pytest.mark.parametrize("P", [368, 380, 1000])
+def test_fused_acquisition_shared_memory_budget(P):
+    """The fused epilogue keeps the front's stripes beside the operand rings.  At d = 12 about 3 KB are free: P = 368
+    fits together with the step schedule, P = 380 only with the schedule left in global memory, P = 1000 not at all
+    (the unfused sequence runs).  Same results in all three cases."""
     if not _cabi.fast_path_available():
         pytest.skip("fast path not built")
     n, d, m = 1024, 12, 4096
     X, Y, ells, sf2 = make_problem(n, d)
-    t = np.linspace(0.0, 1.0, n)
-    Y = np.column_stack([t, 1.0 - t]) + 1e-5 * Y          # every training point on the first front
-    models = [ob.GPModel(X, Y[:, i], ells[i], sf2[i], device=DEV) for i in range(2)]
-    PF, r = ob.host_prep.calc_pf(Y), Y.max(0) + 0.1
-    assert len(PF) > 900
+    t = np.linspace(0.0, 1.0, P)
+    Yf = np.column_stack([t, 1.0 - t])                     # P points on the first front ...
+    Yd = 1.5 + 0.1 * np.abs(Y[: n - P] / np.abs(Y).max())  # ... the rest dominated by all of them
+    Y2 = np.vstack([Yf, Yd]) + 1e-7 * Y
+    models = [ob.GPModel(X, Y2[:, i], ells[i], sf2[i], device=DEV) for i in range(2)]
+    PF, r = ob.host_prep.calc_pf(Y2), Y2.max(0) + 0.1
+    assert len(PF) == P
     spec = ob.spec_ehvi(r, PF, ob.host_prep.cached_samples(2, 5, seed=0), "exact")
     pool = ob.CandidatePool.counter(m, np.zeros(d), np.ones(d), seed=3)
+    before = _cabi.Context.get(0).launch_count()
     a = ob.score(models, spec, pool, precision="fast", want_acq=True)
+    n_a = _cabi.Context.get(0).launch_count() - before
     b = ob.score(models, spec, pool, precision="fast", want_acq=True, want_posterior=True)
+    n_b = _cabi.Context.get(0).launch_count() - before - n_a
+    if all(g.plane_format == "f8c" for g in models):
+        assert (n_a < n_b) == (P < 384)                    # fused exactly while the stripes fit
     np.testing.assert_array_equal(a.acq.cpu().numpy(), b.acq.cpu().numpy())
     assert (a.best_index, a.best_value) == (b.best_index, b.best_value)
 
