@@ -153,14 +153,15 @@ __global__ void __launch_bounds__(256) k_syrk_update(double *__restrict__ A, int
 }
 
 // ------------------------------------------------------------------------------------------
-// triangular inverse, 16 columns per CTA.  X = L^-1, block row by block row:
+// triangular inverse, TC columns per CTA.  X = L^-1, block row by block row:
 //   T = I[ib rows, these columns] - sum_{jb < ib} L[ib][jb] X[jb],   X[ib] = Dinv[ib] T
 // The CTA walks the tile products (ib, jb = kb .. ib-1) and the diagonal product (ib, jb = ib) as ONE sequence of
 // steps and double-buffers their operands with cp.async: the 32 KB tile of L (or of Dinv) and the 64 x 16 tile of X for
 // step s + 1 arrive while step s multiplies (round 1 loaded them between two barriers, and the first column block
 // runs 120 + 16 such steps back to back).  Every sum keeps its order (jb ascending, then t ascending), so the result is
 // bit-identical to the unpipelined kernel.
-#define TC 16
+#define TC 8       // columns per CTA: n_pad / 8 CTAs (128 at n = 1024, one per SM); 16 halves the CTAs and doubles the chain
+#define TCV (TC / 4) // columns per thread
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem));
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(256) k_trtri_cols(const double *__restrict__ L
   const int c0 = blockIdx.x * TC;
   const int kb = c0 / NB;
   const int r = tid % NB;          // output row inside the block row
-  const int cg = (tid / NB) * 4;   // first of 4 output columns
+  const int cg = (tid / NB) * TCV; // first of this thread's output columns
   auto issue = [&](int ib, int jb, int buf, bool with_x) {
     const double *src = jb < ib ? L + ((size_t)ib * NB) * ld + (size_t)jb * NB : dinv + (size_t)ib * NB * NB;
     const int stride = jb < ib ? ld : NB;
@@ -187,9 +188,9 @@ __global__ void __launch_bounds__(256) k_trtri_cols(const double *__restrict__ L
   };
   int ib = kb, jb = kb, buf = 0;
   issue(ib, jb, 0, false);
-  double T[4];
+  double T[TCV];
 #pragma unroll
-  for (int v = 0; v < 4; ++v) T[v] = (ib * NB + r == c0 + cg + v) ? 1.0 : 0.0;
+  for (int v = 0; v < TCV; ++v) T[v] = (ib * NB + r == c0 + cg + v) ? 1.0 : 0.0;
   while (ib < nb) {
     const int nib = jb < ib ? ib : ib + 1, njb = jb < ib ? jb + 1 : kb;
     const bool has_next = nib < nb;
@@ -212,25 +213,27 @@ __global__ void __launch_bounds__(256) k_trtri_cols(const double *__restrict__ L
       for (int t = 0; t < NB; ++t) {
         double l = Lb[buf][r][t];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) T[v] -= l * Xb[buf][t][cg + v];
+        for (int v = 0; v < TCV; ++v) T[v] -= l * Xb[buf][t][cg + v];
       }
     } else {
       // X_ib = Dinv_ib * T
 #pragma unroll
-      for (int v = 0; v < 4; ++v) Xb[buf][r][cg + v] = T[v];
+      for (int v = 0; v < TCV; ++v) Xb[buf][r][cg + v] = T[v];
       __syncthreads();
-      double o[4] = {0, 0, 0, 0};
+      double o[TCV];
+#pragma unroll
+      for (int v = 0; v < TCV; ++v) o[v] = 0.0;
 #pragma unroll 8
       for (int t = 0; t < NB; ++t) {
         double l = Lb[buf][r][t];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) o[v] += l * Xb[buf][t][cg + v];
+        for (int v = 0; v < TCV; ++v) o[v] += l * Xb[buf][t][cg + v];
       }
 #pragma unroll
-      for (int v = 0; v < 4; ++v) Linv[((size_t)ib * NB + r) * ld + c0 + cg + v] = o[v];
+      for (int v = 0; v < TCV; ++v) Linv[((size_t)ib * NB + r) * ld + c0 + cg + v] = o[v];
       __threadfence_block();
 #pragma unroll
-      for (int v = 0; v < 4; ++v) T[v] = ((ib + 1) * NB + r == c0 + cg + v) ? 1.0 : 0.0;
+      for (int v = 0; v < TCV; ++v) T[v] = ((ib + 1) * NB + r == c0 + cg + v) ? 1.0 : 0.0;
     }
     __syncthreads();
     ib = nib; jb = njb; buf ^= 1;
