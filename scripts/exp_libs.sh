@@ -4,7 +4,7 @@ TAG=$1; shift
 B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-fit --no-e2e --no-extras"
 for rep in 1 2; do
   for lib in "$@"; do
-    cp scripts/trace_lib/$lib optimobo_b200/liboptimobo_b200.so
+    mkdir -p scripts/trace_lib; cp scripts/trace_lib/$lib optimobo_b200/liboptimobo_b200.so
     timeout 90 $B > gpurun_out/${TAG}_${lib}_$rep.json 2> gpurun_out/${TAG}_${lib}_$rep.err
     python - <<PY
 import json
