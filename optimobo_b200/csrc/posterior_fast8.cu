@@ -80,6 +80,15 @@ __device__ __forceinline__ uint32_t ld_acquire_shared(uint32_t a) {
 __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};\n" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
+// the same with a compile-time byte offset folded into the instruction (no address arithmetic per store)
+template <int OFF>
+__device__ __forceinline__ void sts128_at(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0+%5], {%1, %2, %3, %4};\n" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w), "n"(OFF) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void sts64_at(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.b32 [%0+%3], {%1, %2};\n" ::"r"(a), "r"(x), "r"(y), "n"(OFF) : "memory");
+}
 
 #define F8_TRACE_N 8192
 #ifndef F8_TRACING
@@ -205,7 +214,7 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
   if (GW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
   if (warp == 0) {
     // =============================== B producer (both CTAs) ===============================
-    if (elect_one()) {
+    if (elect_one() && !(prm.dbg & 128)) {
       uint32_t st = 0, ph = 0;
       long long w_bempty = 0; const long long t_start = clock64();
       for (long long it = 0; it < n_iter; ++it) {
@@ -242,7 +251,7 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
     }
   } else if (warp == 1) {
     // =============================== MMA issuer (leader CTA) ==============================
-    if (leader && elect_one()) {
+    if (leader && elect_one() && !(prm.dbg & 128)) {
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, tph = 0;
       long long w_afull = 0, w_bfull = 0, w_tempty = 0;
       for (long long it = 0; it < n_iter; ++it) {
@@ -325,7 +334,7 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
     //     Either way the thread then arrives on a_empty: a stage is free once the MMA has consumed it AND the cache
     //     copy has read it.  (Measured alternatives, all slower: reloads issued by the B producer -- blocking or
     //     polling both cursors --, or by a generator thread when it passes the step.)
-    if (elect_one()) {
+    if (elect_one() && !(prm.dbg & 128)) {
       long long it_s = 0; int i_s = 0;
       bool s_done = n_iter == 0;
       uint32_t sl = 0, slph = 0;
@@ -400,7 +409,7 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
     const uint32_t t_empty_leader = mapa_rank(smem_u32(&t_empty[0]), 0);
     BestPair best;                               // fused acquisition: this thread's running arg-max
     best.v = -INFINITY; best.i = 0x7fffffffffffffffLL;
-    for (long long it = 0; it < n_iter; ++it) {
+    for (long long it = 0; it < ((prm.dbg & 128) ? 0 : n_iter); ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
       const long long cg = tile * FM + row;
       // the other model's posterior of this candidate: requested now, needed after the tile's last chunk
@@ -494,13 +503,13 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
     // (the kernel function is a template parameter: a run-time branch per row splits the block body into basic
     // blocks and the scheduler cannot interleave one row's MUFU chain with the next row's FFMA2s / conversions)
     constexpr int ROWS = R;
-    uint32_t off_hi[ROWS], off_c8[ROWS];
-#pragma unroll
-    for (int rr = 0; rr < ROWS; ++rr) {
-      const int row = row0 + 16 * rr;
-      off_hi[rr] = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (((g ^ (row & 7)) & 7) << 4));
-      off_c8[rr] = (uint32_t)((row >> 3) * 512 + (row & 7) * 64 + ((((g >> 1) ^ (row >> 1)) & 3) << 4) + (g & 1) * 8);
-    }
+    // swizzled store offsets of this lane's first row; its other rows are 16 apart, which leaves (row & 7) and
+    // (row >> 1) & 3 -- the swizzle terms -- unchanged: row r0 + 16 rr sits exactly 2048 rr (fp16 plane) / 1024 rr (e4m3
+    // planes) bytes further.  Written out as immediates of the stores: with an offset array the compiler re-derived
+    // all eight offsets from the lane bits in every K-block (~85 integer instructions of 690, none in the
+    // stand-alone loop of scripts/k1_loop_bench.cu).
+    const uint32_t off_hi0 = (uint32_t)((row0 >> 3) * 1024 + (row0 & 7) * 128 + (((g ^ (row0 & 7)) & 7) << 4));
+    const uint32_t off_c80 = (uint32_t)((row0 >> 3) * 512 + (row0 & 7) * 64 + ((((g >> 1) ^ (row0 >> 1)) & 3) << 4) + (g & 1) * 8);
     const uint32_t sA_u = smem_u32(sA);
     const uint32_t a_empty_u = smem_u32(a_empty), a_written_u = smem_u32(a_written);
     const uint32_t s_full_u = smem_u32(s_full), s_empty_u = smem_u32(s_empty);
@@ -510,6 +519,9 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
     const int trole = (lane == 0) ? (gw == 0 ? 5 : (gw == 5 ? 6 : (gw == GW - 1 ? 7 : -1))) : -1;
 #endif
     if (prm.dbg & 8) __nanosleep(400u * (unsigned)rg);       // experiment: start the row groups out of phase
+    // timing experiment (results are garbage): bit 7 = the generator loop alone, every other role idle and no barrier
+    // traffic except the candidate coordinates; bit 8 = without the proxy fence as well
+    const bool solo = (prm.dbg & 128) != 0;
     for (long long it = 0; it < n_iter; ++it) {
       const long long tile = blockIdx.x + it * gridDim.x;
       const int b = (int)(it & 1);
@@ -535,15 +547,16 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
             // a K* block streamed back from the cache (by warp 3).  Every generator warp still waits for the stage's
             // release: a warp that skipped ahead through a run of reloads would get more than one barrier
             // phase ahead of the MMA, and a parity wait cannot tell phases two apart.
-            mbar_wait_sleep(a_empty_u + sa * 8, pa ^ 1, 128);
+            if (!solo) mbar_wait_sleep(a_empty_u + sa * 8, pa ^ 1, 128);
             if (++sa == NSTA) { sa = 0; pa ^= 1; }
             continue;
           }
           F8_TRACE_G(kb);
-          mbar_wait_sleep(s_full_u + sl * 8, slph, 20);                       // this block's train slice has landed
+          if (!solo) mbar_wait_sleep(s_full_u + sl * 8, slph, 20);            // this block's train slice has landed
           F8_TRACE_G(0x40 | kb);
           const float *xs = xt + sl * XT_STRIDE + 8 * g;
           const uint32_t st_u = sA_u + sa * STAGE_BYTES;
+          const uint32_t st_hi = st_u + off_hi0, st_c8 = st_u + off_c80;
           if (!(prm.dbg & 2)) {
             float2 r2[ROWS][4];
             {
@@ -574,7 +587,7 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
             const float4 al0 = *(const float4 *)(xs + DP * FK);
             const float4 al1 = *(const float4 *)(xs + DP * FK + 4);
             F8_TRACE_G(0x80 | kb);
-            mbar_wait_sleep(a_empty_u + sa * 8, pa ^ 1, 32);                   // stage released (MMA + cache copy)
+            if (!solo) mbar_wait_sleep(a_empty_u + sa * 8, pa ^ 1, 32);        // stage released (MMA + cache copy)
             F8_TRACE_G(0xC0 | kb);
 #pragma unroll
             for (int rr = 0; rr < ROWS; ++rr) {
@@ -622,17 +635,19 @@ k_posterior_fast8(const __grid_constant__ F8Maps maps, const FastParams prm) {
                 if (e & 1) { c1[e >> 1] |= l8 << 16; c2[e >> 1] |= a8 << 16; }
                 else { c1[e >> 1] = l8; c2[e >> 1] = a8; }
               }
-              sts128(st_u + off_hi[rr], hi[0], hi[1], hi[2], hi[3]);
-              sts64(st_u + F8_OFF_C1 + off_c8[rr], c1[0], c1[1]);
-              sts64(st_u + F8_OFF_C2 + off_c8[rr], c2[0], c2[1]);
+              // (rr is a compile-time index of the unrolled row loop)
+              if (rr == 0) { sts128_at<0>(st_hi, hi[0], hi[1], hi[2], hi[3]); sts64_at<F8_OFF_C1>(st_c8, c1[0], c1[1]); sts64_at<F8_OFF_C2>(st_c8, c2[0], c2[1]); }
+              else if (rr == 1) { sts128_at<2048>(st_hi, hi[0], hi[1], hi[2], hi[3]); sts64_at<F8_OFF_C1 + 1024>(st_c8, c1[0], c1[1]); sts64_at<F8_OFF_C2 + 1024>(st_c8, c2[0], c2[1]); }
+              else if (rr == 2) { sts128_at<4096>(st_hi, hi[0], hi[1], hi[2], hi[3]); sts64_at<F8_OFF_C1 + 2048>(st_c8, c1[0], c1[1]); sts64_at<F8_OFF_C2 + 2048>(st_c8, c2[0], c2[1]); }
+              else { sts128_at<6144>(st_hi, hi[0], hi[1], hi[2], hi[3]); sts64_at<F8_OFF_C1 + 3072>(st_c8, c1[0], c1[1]); sts64_at<F8_OFF_C2 + 3072>(st_c8, c2[0], c2[1]); }
             }
           } else {
             mbar_wait_sleep(a_empty_u + sa * 8, pa ^ 1, 32);
           }
-          fence_proxy_async_smem();
+          if (!(prm.dbg & 256)) fence_proxy_async_smem();
           __syncwarp();
           F8_TRACE_G(0x20 | kb);
-          if (lane == 0) {
+          if (lane == 0 && !solo) {
             mbar_arrive(s_empty_u + sl * 8);                                   // slice free
             mbar_arrive_remote(a_full_leader0 + sa * 8);                       // the leader's MMA consumes both halves
             mbar_arrive(a_written_u + sa * 8);                                 // this CTA's cache copy may start
