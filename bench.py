@@ -70,7 +70,9 @@ def issued_units_per_mac(fmt):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clock, power and clock-event (throttle) reasons during the timed region: NVML every 20 ms when
+    pynvml is importable (the same counters nvidia-smi prints), else the nvidia-smi query of the profiling recipe
+    (one subprocess per sample, ~5 per second).  Also reads NVML's total-energy counter at both ends."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -79,18 +81,49 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu, self.rows, self._stop_ev = gpu_index, [], threading.Event()
+        self.nv, self.h, self.e0, self.energy_j = None, None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = int(vis.split(",")[gpu_index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.e0 = pynvml.nvmlDeviceGetTotalEnergyConsumption(self.h)
+        except Exception:
+            self.nv = None
+
+    def _nvml_row(self):
+        nv, h = self.nv, self.h
+        try:
+            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        flag = lambda bit: "Active" if reasons & bit else "Not Active"
+        return [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)),
+                str(nv.nvmlDeviceGetPowerUsage(h) / 1e3), hex(reasons),
+                flag(0x8), flag(0x40), flag(0x20), flag(0x4)]      # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
 
     def run(self):
         while not self._stop_ev.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nv is not None:
+                    self.rows.append(self._nvml_row())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                         timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop_ev.wait(0.2)
+            self._stop_ev.wait(0.02 if self.nv is not None else 0.2)
+        if self.nv is not None and self.e0 is not None:
+            try:
+                self.energy_j = (self.nv.nvmlDeviceGetTotalEnergyConsumption(self.h) - self.e0) / 1e3
+            except Exception:
+                pass
 
     def summary(self):
         self._stop_ev.set()
@@ -106,7 +139,8 @@ class ClockSampler(threading.Thread):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
                 "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons), "source": "nvml" if self.nv is not None else "nvidia-smi",
+                "energy_j": self.energy_j}
 
 
 def cpu_oracle_rate(budget_s, chunk=4096, semantics="exact"):
@@ -349,6 +383,10 @@ def main():
     wall = time.perf_counter() - wall0
     launches = ctx.launch_count(reset=True)
     clocks = sampler.summary() if sampler else None
+    if clocks and clocks.get("energy_j") is not None:
+        # NVML total-energy counter over the timed region (the kernel runs at the power cap: time follows energy);
+        # includes the 256 MB L2 flush between steps
+        clocks["energy_j_per_step"] = clocks.pop("energy_j") / args.steps
     value = m_total * args.steps / (total_ms / 1e3)
 
     # ---- end-to-end: host candidates through the C-ABI host entry ------------------------------
