@@ -111,7 +111,10 @@ k_posterior_fp64(GpDev gp, PoolDev pool, long long m, double *__restrict__ scrat
     __syncthreads();
 
     // ---------------- phase B: V = K* . Linv^T, fused sum of squares ---------------------
-    const int wm = warp >> 2, wn = warp & 3;
+    // warp w runs on scheduler w & 3.  The second row of warps takes its column groups in reverse, so that every
+    // scheduler hosts column groups {q, 3 - q}: in the diagonal steps below group q multiplies q + 1 quarters of the
+    // K range, and with the plain map all of the long ones sat on scheduler 3
+    const int wm = warp >> 2, wn = wm == 0 ? (warp & 3) : 3 - (warp & 3);
     const int g8 = lane >> 2, t4 = lane & 3;
     double ss[4] = {0.0, 0.0, 0.0, 0.0};
     for (int j0 = 0; j0 < (want_var ? np : 0); j0 += NC) {
@@ -136,11 +139,7 @@ k_posterior_fp64(GpDev gp, PoolDev pool, long long m, double *__restrict__ scrat
         }
         cp_async_commit();
       };
-      issue(0, 0);
-      for (int ks = 0; ks < steps; ++ks) {
-        const int buf = ks & 1;
-        if (ks + 1 < steps) { issue(ks + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-        __syncthreads();
+      auto mma_step = [&](int buf) {
         const double *Ab = As + (size_t)buf * TM * SROW + (size_t)(32 * wm + g8) * SROW + t4;
         const double *Bb = Bs + (size_t)buf * NC * SROW + (size_t)(32 * wn + g8) * SROW + t4;
 #pragma unroll
@@ -153,6 +152,26 @@ k_posterior_fp64(GpDev gp, PoolDev pool, long long m, double *__restrict__ scrat
 #pragma unroll
             for (int v = 0; v < 4; ++v) dmma884(acc[u][v][0], acc[u][v][1], a[u], b[v]);
         }
+      };
+      // k < j0: every warp multiplies.  The last 128 / KC steps run through the diagonal block of L^-1, where the warp
+      // holding columns [j0 + 32 wn, + 32) only needs k < j0 + 32 wn + 32 (the rest of its B rows is zero): a separate
+      // loop, so that the main loop stays free of the per-warp branch
+      const int steps_all = j0 / KC, my_steps = (j0 + 32 * wn + 32) / KC;
+      issue(0, 0);
+      int ks = 0;
+      for (; ks < steps_all; ++ks) {
+        const int buf = ks & 1;
+        issue(ks + 1, buf ^ 1);                   // (steps_all < steps: there is always a next step here)
+        cp_async_wait<1>();
+        __syncthreads();
+        mma_step(buf);
+        __syncthreads();
+      }
+      for (; ks < steps; ++ks) {
+        const int buf = ks & 1;
+        if (ks + 1 < steps) { issue(ks + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();
+        if (ks < my_steps) mma_step(buf);
         __syncthreads();
       }
 #pragma unroll
