@@ -386,7 +386,9 @@ def main():
     if clocks and clocks.get("energy_j") is not None:
         # NVML total-energy counter over the timed region (the kernel runs at the power cap: time follows energy);
         # includes the 256 MB L2 flush between steps
-        clocks["energy_j_per_step"] = clocks.pop("energy_j") / args.steps
+        # (the counter advances in coarse ticks: below about a second of timed region the figure is noise)
+        e_j = clocks.pop("energy_j")
+        clocks["energy_j_per_step"] = e_j / args.steps if wall >= 1.0 else None
     value = m_total * args.steps / (total_ms / 1e3)
 
     # ---- end-to-end: host candidates through the C-ABI host entry ------------------------------
