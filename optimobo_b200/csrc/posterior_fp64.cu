@@ -10,7 +10,9 @@
 //                 mu_c = sum_i k*[c][i] alpha[i] accumulated on the way;
 //   phase B (K2): V = K* . L^-T on the FP64 tensor pipe (mma.sync m8n8k4 DMMA), 128 columns of
 //                 L^-1 at a time, K-loop stopped at the diagonal (L^-1 is lower triangular, so
-//                 only ~n^2/2 MACs per candidate are issued); the epilogue squares and
+//                 only ~n^2/2 MACs per candidate are issued), and inside the diagonal 128 x 128 block every
+//                 warp stops at the end of ITS 32 columns -- with the warps mapped so that each of the four
+//                 schedulers hosts one short and one long column group; the epilogue squares and
 //                 row-reduces the accumulators, so only sum_j v_j^2 per candidate survives:
 //                 var = max(sigma_f2 - sum_j v_j^2, floor) + sigma_n2.
 // tcgen05 has no f64 kind, so the FP64 path is mma.sync by necessity.
